@@ -1,0 +1,70 @@
+"""ctypes binding of the C-ABI library (include/elliot_b200.h).
+
+There is NO fallback: if the shared library is missing, or no CUDA device is present when a
+compute entry point is called, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libelliot_b200.so")
+
+c_i32, c_i64, c_u64, c_f32, c_f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_double
+c_int, c_void, c_size = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/elliot_b200.h one to one
+SIGNATURES = {
+    "eb_last_error": (ctypes.c_char_p, []),
+    "eb_version": (c_int, []),
+    "eb_device_info": (c_int, [c_void, c_void]),
+    "eb_bpr_step_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
+                                c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_int, c_void]),
+    "eb_bpr_step_sampled_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i32, c_i32, c_void, c_void,
+                                        c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32,
+                                        c_void, c_void, c_void, c_void, c_int, c_void]),
+    "eb_bpr_sample_philox": (c_int, [c_i32, c_i32, c_void, c_void, c_i64, c_u64, c_u64, c_void, c_void, c_void,
+                                     c_void]),
+    "eb_bpr_step_host_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
+                                     c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void, c_int, c_void]),
+    "eb_bpr_exact_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
+    "eb_bpr_exact_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i32, c_i32, c_void, c_void, c_void, c_i64,
+                                 c_f64, c_f64, c_f64, c_f64, c_f64, c_void, c_void, c_size, c_void]),
+    "eb_mt_seed": (c_int, [c_void, ctypes.c_uint32, c_void]),
+    "eb_mt_sampler_workspace_bytes": (c_size, [c_i64]),
+    "eb_mt_sampler_step": (c_int, [c_void, c_i32, c_i32, c_void, c_void, c_void, c_i64, c_void, c_void, c_void,
+                                   c_void, c_size, c_void]),
+    "eb_mt_raw": (c_int, [c_void, c_void, c_i64, c_void]),
+    "eb_score_topk_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),
+    "eb_score_topk_f32": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_void, c_i32, c_i64,
+                                  c_int, c_void, c_void, c_void, c_size, c_void]),
+    "eb_score_topk_f64": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_void, c_i32, c_i64,
+                                  c_int, c_void, c_void, c_void, c_size, c_void]),
+}
+
+_lib = None
+
+
+class EbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libelliot_b200.so (built by `python -m elliot_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EbError(f"{LIB_PATH} is missing: build it with `python -m elliot_b200.build` "
+                          f"(there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().eb_last_error().decode("utf-8", "replace")
+        raise EbError(f"elliot_b200 C-ABI error {rc}: {msg}")

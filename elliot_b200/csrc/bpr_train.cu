@@ -1,0 +1,506 @@
+// bpr_train.cu — fused BPR-MF training step kernels (sm_100a).
+//
+// Replaces MFModel.train_step/update_factors
+// (elliot/recommender/latent_factor_models/BPRMF/BPRMF_model.py:87-117) and, in the
+// sampled variant, Sampler.step (elliot/dataset/samplers/custom_sampler.py:24-46).
+//
+//  * bpr_hogwild_kernel  — throughput mode, fp32.  A group of G = d/4 lanes owns one
+//    triple: 128-bit loads of the three embedding rows, warp-shuffle reduction of the
+//    two dot products, log-sigmoid gradient, 128-bit vector atomics (REDG.F32x4) for
+//    the scatter-add.  Each lane of a warp first fetches/samples ONE triple (coalesced
+//    index loads or Philox), the groups then walk the warp's 32 triples with shuffles,
+//    prefetching the next triple's rows while the current one is reduced.
+//  * bpr_exact_kernel    — exact mode, fp64.  Same arithmetic, but sequentially
+//    consistent with the array order of the triples: every row carries a turn counter,
+//    a triple waits until each of its three rows has seen exactly the touches that
+//    precede it in the sequence (ranks come from a radix sort of (row, position)).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace eb {
+
+struct HogwildParams {
+    float *U, *V, *b;
+    int ld;
+    const int32_t *tu, *ti, *tj;
+    int64_t n;
+    float lr, reg_u, reg_b, reg_pos, reg_neg;
+    double *loss;
+    // sampler
+    int32_t n_users, n_items;
+    const int64_t *indptr;
+    const int32_t *indices;
+    uint64_t seed, first;
+    int32_t *out_u, *out_i, *out_j;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// u uniform over users, i uniform over the user's train items, j uniform over the
+// complement (rejection against the sorted CSR row) — custom_sampler.py:31-42 semantics,
+// Philox stream instead of MT19937.
+__device__ __forceinline__ void sample_triple(const HogwildParams &p, int64_t t, int &u, int &i, int &j) {
+    uint32_t r[4];
+    Philox::gen(p.seed, p.first + (uint64_t)t, 0u, r);
+    u = (int)bounded(r[0], (uint32_t)p.n_users);
+    int64_t beg = __ldg(p.indptr + u), end = __ldg(p.indptr + u + 1);
+    int len = (int)(end - beg);
+    uint32_t attempt = 0;
+    while (len == 0) {  // users without train items never appear in the reference's dict
+        Philox::gen(p.seed, p.first + (uint64_t)t, ++attempt | 0x80000000u, r);
+        u = (int)bounded(r[0], (uint32_t)p.n_users);
+        beg = __ldg(p.indptr + u); end = __ldg(p.indptr + u + 1); len = (int)(end - beg);
+    }
+    const int32_t *row = p.indices + beg;
+    i = __ldg(row + bounded(r[1], (uint32_t)len));
+    int cand = (int)bounded(r[2], (uint32_t)p.n_items);
+    if (!contains_sorted(row, len, cand)) { j = cand; return; }
+    cand = (int)bounded(r[3], (uint32_t)p.n_items);
+    attempt = 0;
+    int q = 4;
+    while (contains_sorted(row, len, cand) && attempt < 4096u) {
+        if (q == 4) { Philox::gen(p.seed, p.first + (uint64_t)t, ++attempt, r); q = 0; }
+        cand = (int)bounded(r[q++], (uint32_t)p.n_items);
+    }
+    j = cand;
+}
+
+template <int VPL>
+struct Rows {
+    float4 u[VPL], vi[VPL], vj[VPL];
+    float bi, bj;
+};
+
+template <int DP, bool SAMPLE, bool ATOMIC>
+__global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p) {
+    constexpr int NV = DP / 4;                 // float4 per row
+    constexpr int G = NV >= 32 ? 32 : NV;      // lanes per triple
+    constexpr int VPL = NV / G;                // float4 per lane
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gbase = lane - gl;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t ld = p.ld;
+    float loss_acc = 0.f;
+
+    auto load_rows = [&](Rows<VPL> &r, int u, int i, int j) {
+        if (u >= 0) {
+            const float4 *pu = reinterpret_cast<const float4 *>(p.U + (int64_t)u * ld);
+            const float4 *pi = reinterpret_cast<const float4 *>(p.V + (int64_t)i * ld);
+            const float4 *pj = reinterpret_cast<const float4 *>(p.V + (int64_t)j * ld);
+#pragma unroll
+            for (int v = 0; v < VPL; v++) {
+                r.u[v] = pu[v * G + gl];
+                r.vi[v] = pi[v * G + gl];
+                r.vj[v] = pj[v * G + gl];
+            }
+            r.bi = p.b[i];
+            r.bj = p.b[j];
+        }
+    };
+
+    for (int64_t tile = warp_id; tile * 32 < p.n; tile += nwarps) {
+        const int64_t t = tile * 32 + lane;
+        int u = -1, i = 0, j = 0;
+        if (t < p.n) {
+            if (SAMPLE) {
+                sample_triple(p, t, u, i, j);
+                if (p.out_u) { p.out_u[t] = u; p.out_i[t] = i; p.out_j[t] = j; }
+            } else {
+                u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
+            }
+        }
+        int cu = __shfl_sync(0xffffffffu, u, gbase), ci = __shfl_sync(0xffffffffu, i, gbase),
+            cj = __shfl_sync(0xffffffffu, j, gbase);
+        Rows<VPL> cur;
+        load_rows(cur, cu, ci, cj);
+#pragma unroll
+        for (int s = 0; s < G; s++) {
+            Rows<VPL> nxt;
+            int nu = -1, ni = 0, nj = 0;
+            if (s + 1 < G) {
+                nu = __shfl_sync(0xffffffffu, u, gbase + s + 1);
+                ni = __shfl_sync(0xffffffffu, i, gbase + s + 1);
+                nj = __shfl_sync(0xffffffffu, j, gbase + s + 1);
+                load_rows(nxt, nu, ni, nj);
+            }
+            // ---- score: x = (b_i - b_j) + U[u].(V_i - V_j)
+            float part = 0.f;
+            if (cu >= 0) {
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    part += cur.u[v].x * (cur.vi[v].x - cur.vj[v].x) + cur.u[v].y * (cur.vi[v].y - cur.vj[v].y) +
+                            cur.u[v].z * (cur.vi[v].z - cur.vj[v].z) + cur.u[v].w * (cur.vi[v].w - cur.vj[v].w);
+                }
+            }
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (cu >= 0) {
+                const float x = part + (cur.bi - cur.bj);
+                const float z = __fdividef(1.f, 1.f + __expf(x));  // BPRMF_model.py:98
+                if (gl == 0) loss_acc += fmaxf(-x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
+                float *pu = p.U + (int64_t)cu * ld, *pi = p.V + (int64_t)ci * ld, *pj = p.V + (int64_t)cj * ld;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    const float4 a = cur.u[v], bi4 = cur.vi[v], bj4 = cur.vj[v];
+                    float4 du, di, dj, un;
+                    du.x = p.lr * ((bi4.x - bj4.x) * z - p.reg_u * a.x);
+                    du.y = p.lr * ((bi4.y - bj4.y) * z - p.reg_u * a.y);
+                    du.z = p.lr * ((bi4.z - bj4.z) * z - p.reg_u * a.z);
+                    du.w = p.lr * ((bi4.w - bj4.w) * z - p.reg_u * a.w);
+                    un.x = a.x + du.x; un.y = a.y + du.y; un.z = a.z + du.z; un.w = a.w + du.w;
+                    // item rows see the UPDATED user row (view aliasing, BPRMF_model.py:92,109-116)
+                    di.x = p.lr * (un.x * z - p.reg_pos * bi4.x);
+                    di.y = p.lr * (un.y * z - p.reg_pos * bi4.y);
+                    di.z = p.lr * (un.z * z - p.reg_pos * bi4.z);
+                    di.w = p.lr * (un.w * z - p.reg_pos * bi4.w);
+                    dj.x = p.lr * (-un.x * z - p.reg_neg * bj4.x);
+                    dj.y = p.lr * (-un.y * z - p.reg_neg * bj4.y);
+                    dj.z = p.lr * (-un.z * z - p.reg_neg * bj4.z);
+                    dj.w = p.lr * (-un.w * z - p.reg_neg * bj4.w);
+                    const int e = (v * G + gl) * 4;
+                    if (ATOMIC) {
+                        red_add_v4(pu + e, du);
+                        red_add_v4(pi + e, di);
+                        red_add_v4(pj + e, dj);
+                    } else {
+                        *reinterpret_cast<float4 *>(pu + e) = un;
+                        *reinterpret_cast<float4 *>(pi + e) =
+                            make_float4(bi4.x + di.x, bi4.y + di.y, bi4.z + di.z, bi4.w + di.w);
+                        *reinterpret_cast<float4 *>(pj + e) =
+                            make_float4(bj4.x + dj.x, bj4.y + dj.y, bj4.z + dj.z, bj4.w + dj.w);
+                    }
+                }
+                if (gl == 0) {
+                    const float dbi = p.lr * (z - p.reg_b * cur.bi), dbj = p.lr * (-z - p.reg_b * cur.bj);
+                    if (ATOMIC) { red_add_f32(p.b + ci, dbi); red_add_f32(p.b + cj, dbj); }
+                    else { p.b[ci] = cur.bi + dbi; p.b[cj] = cur.bj + dbj; }
+                }
+            }
+            if (s + 1 < G) { cur = nxt; cu = nu; ci = ni; cj = nj; }
+        }
+    }
+    if (p.loss) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+        if (lane == 0 && loss_acc != 0.f) atomicAdd(p.loss, (double)loss_acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) philox_sample_kernel(const HogwildParams p) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < p.n; t += stride) {
+        int u, i, j;
+        sample_triple(p, t, u, i, j);
+        p.out_u[t] = u; p.out_i[t] = i; p.out_j[t] = j;
+    }
+}
+
+template <int DP, bool SAMPLE, bool ATOMIC>
+static int launch_hogwild_t(const HogwildParams &p, cudaStream_t st) {
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bpr_hogwild_kernel<DP, SAMPLE, ATOMIC>, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t tiles = (p.n + 31) / 32;
+    int64_t want = (tiles + 7) / 8;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    bpr_hogwild_kernel<DP, SAMPLE, ATOMIC><<<(unsigned)grid, 256, 0, st>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+template <bool SAMPLE>
+static int launch_hogwild(const HogwildParams &p, int dp, bool atomic, cudaStream_t st) {
+#define EB_CASE(DPV)                                                                           \
+    case DPV:                                                                                  \
+        return atomic ? launch_hogwild_t<DPV, SAMPLE, true>(p, st) : launch_hogwild_t<DPV, SAMPLE, false>(p, st);
+    switch (dp) {
+        EB_CASE(8) EB_CASE(16) EB_CASE(32) EB_CASE(64) EB_CASE(128) EB_CASE(256)
+        default: return set_err(EB_ERR_ARG, "row stride ld=%d must be one of 8,16,32,64,128,256 floats", dp);
+    }
+#undef EB_CASE
+}
+
+static int check_tables(const void *U, const void *V, const void *b, int d, int ld) {
+    EB_ARG(U && V && b, "null table pointer");
+    EB_ARG(d >= 1 && ld >= d, "need 1 <= d <= ld (d=%d ld=%d)", d, ld);
+    EB_ARG(((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0, "tables must be 16-byte aligned");
+    return EB_OK;
+}
+
+// ---------------------------------------------------------------- exact mode (fp64)
+struct ExactParams {
+    double *U, *V, *b;
+    int d, ld;
+    const int32_t *tu, *ti, *tj;
+    const int32_t *ku, *ki, *kj;
+    int32_t *cntU, *cntI, *ticket;
+    int64_t n;
+    double lr, reg_u, reg_b, reg_pos, reg_neg;
+    double *loss;
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NE>  // elements per lane, d <= 32*NE
+__global__ void __launch_bounds__(128) bpr_exact_kernel(const ExactParams p) {
+    const int lane = threadIdx.x & 31;
+    double loss_acc = 0.0;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(p.ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= p.n) break;
+        const int u = __ldg(p.tu + t), i = __ldg(p.ti + t), j = __ldg(p.tj + t);
+        int32_t *cnt = nullptr;
+        int want = 0;
+        if (lane == 0) { cnt = p.cntU + u; want = __ldg(p.ku + t); }
+        else if (lane == 1) { cnt = p.cntI + i; want = __ldg(p.ki + t); }
+        else if (lane == 2) { cnt = p.cntI + j; want = __ldg(p.kj + t); }
+        if (lane < 3) {
+            unsigned ns = 8;
+            while (ld_acquire(cnt) != want) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
+        }
+        __syncwarp();
+        double *pu = p.U + (int64_t)u * p.ld, *pi = p.V + (int64_t)i * p.ld, *pj = p.V + (int64_t)j * p.ld;
+        double a[NE], vi[NE], vj[NE];
+        double xi = 0.0, xj = 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            const int k = lane + 32 * e;
+            if (k < p.d) {
+                a[e] = __ldcg(pu + k); vi[e] = __ldcg(pi + k); vj[e] = __ldcg(pj + k);
+                xi = __dadd_rn(xi, __dmul_rn(a[e], vi[e]));
+                xj = __dadd_rn(xj, __dmul_rn(a[e], vj[e]));
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            xi = __dadd_rn(xi, __shfl_xor_sync(0xffffffffu, xi, off));
+            xj = __dadd_rn(xj, __shfl_xor_sync(0xffffffffu, xj, off));
+        }
+        const double bi = __ldcg(p.b + i), bj = __ldcg(p.b + j);
+        xi = __dadd_rn(xi, bi);
+        xj = __dadd_rn(xj, bj);
+        const double x = __dadd_rn(xi, -xj);
+        const double z = 1.0 / (1.0 + exp(x));  // BPRMF_model.py:98
+        if (lane == 0) loss_acc += (x > 0) ? log1p(exp(-x)) : (-x + log1p(exp(x)));
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            const int k = lane + 32 * e;
+            if (k < p.d) {
+                // d_u = (V_i - V_j) z - reg_u U[u];  U[u] += lr d_u   (BPRMF_model.py:108-109)
+                const double un = __dadd_rn(
+                    a[e], __dmul_rn(p.lr, __dadd_rn(__dmul_rn(__dadd_rn(vi[e], -vj[e]), z), -__dmul_rn(p.reg_u, a[e]))));
+                // d_i = U'[u] z - reg_pos V_i (BPRMF_model.py:112-113), d_j = -U'[u] z - reg_neg V_j (:116-117)
+                const double uz = __dmul_rn(un, z);
+                const double in_ = __dadd_rn(vi[e], __dmul_rn(p.lr, __dadd_rn(uz, -__dmul_rn(p.reg_pos, vi[e]))));
+                const double jn = __dadd_rn(vj[e], __dmul_rn(p.lr, __dadd_rn(-uz, -__dmul_rn(p.reg_neg, vj[e]))));
+                __stcg(pu + k, un); __stcg(pi + k, in_); __stcg(pj + k, jn);
+            }
+        }
+        if (lane == 0) {
+            __stcg(p.b + i, __dadd_rn(bi, __dmul_rn(p.lr, __dadd_rn(z, -__dmul_rn(p.reg_b, bi)))));
+            __stcg(p.b + j, __dadd_rn(bj, __dmul_rn(p.lr, __dadd_rn(-z, -__dmul_rn(p.reg_b, bj)))));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane < 3) st_release(cnt, want + 1);
+    }
+    if (p.loss && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss, loss_acc);
+}
+
+// keys: (row << ebits) | event ; events of table `which`: users -> event = t, items -> event = 2t+slot
+__global__ void make_keys_kernel(const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n, int ebits,
+                                 uint64_t *keysU, uint64_t *keysI) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    keysU[t] = ((uint64_t)(uint32_t)tu[t] << ebits) | (uint64_t)t;
+    keysI[2 * t] = ((uint64_t)(uint32_t)ti[t] << ebits) | (uint64_t)(2 * t);
+    keysI[2 * t + 1] = ((uint64_t)(uint32_t)tj[t] << ebits) | (uint64_t)(2 * t + 1);
+}
+
+// rank of each event inside its row segment of the sorted key array
+__global__ void ranks_kernel(const uint64_t *keys, int64_t m, int ebits, int is_items, int32_t *ka, int32_t *kb) {
+    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m) return;
+    const uint64_t key = keys[pos];
+    const uint64_t first = (key >> ebits) << ebits;
+    int64_t lo = 0, hi = pos;  // lower_bound of `first`
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < first) lo = mid + 1; else hi = mid;
+    }
+    const int32_t rank = (int32_t)(pos - lo);
+    const uint64_t ev = key & ((1ull << ebits) - 1);
+    if (!is_items) ka[ev] = rank;
+    else if (ev & 1) kb[ev >> 1] = rank;
+    else ka[ev >> 1] = rank;
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int bits_for(uint64_t v) { int b = 1; while ((v >> b) != 0) b++; return b; }
+
+struct ExactLayout {
+    size_t keys_in, keys_out, ku, ki, kj, cnt, cub, total, cub_bytes;
+};
+
+// keys_in / keys_out hold 3n entries each: user keys in [0,n), item keys in [n,3n)
+static ExactLayout exact_layout(int64_t n, int32_t n_users, int32_t n_items) {
+    ExactLayout L;
+    size_t off = 0;
+    L.keys_in = off; off += align_up(sizeof(uint64_t) * 3 * (size_t)n);
+    L.keys_out = off; off += align_up(sizeof(uint64_t) * 3 * (size_t)n);
+    L.ku = off; off += align_up(sizeof(int32_t) * (size_t)n);
+    L.ki = off; off += align_up(sizeof(int32_t) * (size_t)n);
+    L.kj = off; off += align_up(sizeof(int32_t) * (size_t)n);
+    L.cnt = off; off += align_up(sizeof(int32_t) * ((size_t)n_users + (size_t)n_items + 64));
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cb, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)(2 * n), 0, 64);
+    L.cub_bytes = cb;
+    L.cub = off; off += align_up(cb);
+    L.total = off;
+    return L;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" int eb_bpr_step_f32(float *U, float *V, float *item_bias, int d, int ld, const int32_t *tu,
+                               const int32_t *ti, const int32_t *tj, int64_t n, float lr, float reg_u, float reg_b,
+                               float reg_pos, float reg_neg, double *loss, int flags, void *stream) {
+    if (int rc = check_tables(U, V, item_bias, d, ld)) return rc;
+    EB_ARG(n >= 0, "n < 0");
+    if (n == 0) return EB_OK;
+    EB_ARG(tu && ti && tj, "null triple arrays");
+    HogwildParams p{};
+    p.U = U; p.V = V; p.b = item_bias; p.ld = ld; p.tu = tu; p.ti = ti; p.tj = tj; p.n = n;
+    p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
+    return launch_hogwild<false>(p, ld, !(flags & 1), (cudaStream_t)stream);
+}
+
+extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int d, int ld, int32_t n_users,
+                                       int32_t n_items, const int64_t *csr_indptr, const int32_t *csr_indices,
+                                       int64_t n, uint64_t seed, uint64_t first_triple, float lr, float reg_u,
+                                       float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
+                                       int32_t *out_i, int32_t *out_j, int flags, void *stream) {
+    if (int rc = check_tables(U, V, item_bias, d, ld)) return rc;
+    EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
+    EB_ARG(csr_indptr && csr_indices, "null CSR");
+    EB_ARG((!out_u && !out_i && !out_j) || (out_u && out_i && out_j), "out_u/out_i/out_j: all or none");
+    if (n == 0) return EB_OK;
+    HogwildParams p{};
+    p.U = U; p.V = V; p.b = item_bias; p.ld = ld; p.n = n;
+    p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
+    p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
+    p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    return launch_hogwild<true>(p, ld, !(flags & 1), (cudaStream_t)stream);
+}
+
+extern "C" int eb_bpr_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
+                                    const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple,
+                                    int32_t *out_u, int32_t *out_i, int32_t *out_j, void *stream) {
+    EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
+    EB_ARG(csr_indptr && csr_indices && out_u && out_i && out_j, "null pointer");
+    if (n == 0) return EB_OK;
+    HogwildParams p{};
+    p.n = n; p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
+    p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    int64_t grid = (n + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    philox_sample_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+extern "C" int eb_bpr_step_host_f32(float *U, float *V, float *item_bias, int d, int ld, const int32_t *tu_host,
+                                    const int32_t *ti_host, const int32_t *tj_host, int64_t n, float lr, float reg_u,
+                                    float reg_b, float reg_pos, float reg_neg, int32_t *staging, double *loss_dev,
+                                    double *loss_host, int flags, void *stream) {
+    EB_ARG(staging && tu_host && ti_host && tj_host, "null host/staging pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    EB_CUDA(cudaMemcpyAsync(staging, tu_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    EB_CUDA(cudaMemcpyAsync(staging + n, ti_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    EB_CUDA(cudaMemcpyAsync(staging + 2 * n, tj_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    if (loss_dev) EB_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(double), st));
+    if (int rc = eb_bpr_step_f32(U, V, item_bias, d, ld, staging, staging + n, staging + 2 * n, n, lr, reg_u, reg_b,
+                                 reg_pos, reg_neg, loss_dev, flags, stream))
+        return rc;
+    if (loss_dev && loss_host)
+        EB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    return EB_OK;
+}
+
+extern "C" size_t eb_bpr_exact_workspace_bytes(int64_t n, int32_t n_users, int32_t n_items) {
+    if (n <= 0) return 256;
+    return exact_layout(n, n_users, n_items).total;
+}
+
+extern "C" int eb_bpr_exact_f64(double *U, double *V, double *item_bias, int d, int ld, int32_t n_users,
+                                int32_t n_items, const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                                double lr, double reg_u, double reg_b, double reg_pos, double reg_neg, double *loss,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    if (int rc = check_tables(U, V, item_bias, d, ld)) return rc;
+    EB_ARG(d <= 256, "exact mode supports d <= 256 (d=%d)", d);
+    EB_ARG(n >= 0 && n < (1ll << 30), "n out of range");
+    if (n == 0) return EB_OK;
+    EB_ARG(tu && ti && tj && workspace, "null pointer");
+    const ExactLayout L = exact_layout(n, n_users, n_items);
+    if (workspace_bytes < L.total)
+        return set_err(EB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    uint64_t *keys_in = (uint64_t *)(ws + L.keys_in), *keys_out = (uint64_t *)(ws + L.keys_out);
+    int32_t *ku = (int32_t *)(ws + L.ku), *ki = (int32_t *)(ws + L.ki), *kj = (int32_t *)(ws + L.kj);
+    int32_t *cnt = (int32_t *)(ws + L.cnt);
+    const int ebits = bits_for((uint64_t)(2 * n));
+    const int rbits_u = bits_for((uint64_t)n_users), rbits_i = bits_for((uint64_t)n_items);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    make_keys_kernel<<<blocks, 256, 0, st>>>(tu, ti, tj, n, ebits, keys_in, keys_in + n);
+    EB_CUDA(cudaGetLastError());
+    size_t cb = L.cub_bytes;
+    EB_CUDA(cub::DeviceRadixSort::SortKeys(ws + L.cub, cb, keys_in, keys_out, n, 0, ebits + rbits_u, st));
+    ranks_kernel<<<blocks, 256, 0, st>>>(keys_out, n, ebits, 0, ku, nullptr);
+    EB_CUDA(cudaGetLastError());
+    cb = L.cub_bytes;
+    EB_CUDA(cub::DeviceRadixSort::SortKeys(ws + L.cub, cb, keys_in + n, keys_out + n, 2 * n, 0, ebits + rbits_i, st));
+    ranks_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>(keys_out + n, 2 * n, ebits, 1, ki, kj);
+    EB_CUDA(cudaGetLastError());
+    EB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)n_users + (size_t)n_items + 64), st));
+    ExactParams p{};
+    p.U = U; p.V = V; p.b = item_bias; p.d = d; p.ld = ld; p.tu = tu; p.ti = ti; p.tj = tj;
+    p.ku = ku; p.ki = ki; p.kj = kj; p.cntU = cnt; p.cntI = cnt + n_users; p.ticket = cnt + n_users + n_items;
+    p.n = n; p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
+    const int ne = (d + 31) / 32;
+    int64_t grid = (int64_t)sm_count() * 4;
+    if (grid * 4 > n) grid = (n + 3) / 4;
+    if (ne <= 1) bpr_exact_kernel<1><<<(unsigned)grid, 128, 0, st>>>(p);
+    else if (ne <= 2) bpr_exact_kernel<2><<<(unsigned)grid, 128, 0, st>>>(p);
+    else if (ne <= 4) bpr_exact_kernel<4><<<(unsigned)grid, 128, 0, st>>>(p);
+    else bpr_exact_kernel<8><<<(unsigned)grid, 128, 0, st>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}

@@ -1,0 +1,74 @@
+// common.cuh — shared helpers for the sm_100a kernels behind include/elliot_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/elliot_b200.h"
+
+namespace eb {
+
+extern thread_local char g_err[512];
+int set_err(int code, const char *fmt, ...);
+
+#define EB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return eb::set_err(EB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
+                               cudaGetErrorString(_e));                                            \
+    } while (0)
+
+#define EB_ARG(cond, ...)                                                                          \
+    do {                                                                                           \
+        if (!(cond)) return eb::set_err(EB_ERR_ARG, __VA_ARGS__);                                  \
+    } while (0)
+
+int sm_count();
+
+// Philox4x32-10 (Salmon et al. 2011).  key = seed, counter = (triple index, attempt).
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
+#else
+        uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
+#endif
+        uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __host__ __device__ static inline void gen(uint64_t seed, uint64_t ctr, uint32_t attempt, uint32_t (&out)[4]) {
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        out[0] = (uint32_t)ctr; out[1] = (uint32_t)(ctr >> 32); out[2] = attempt; out[3] = 0x454c4c49u;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            round(out, k0, k1);
+            k0 += W0; k1 += W1;
+        }
+    }
+};
+
+// uniform integer in [0, n) from a 32-bit word (multiply-high; bias < n / 2^32)
+__host__ __device__ static inline uint32_t bounded(uint32_t r, uint32_t n) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(r, n);
+#else
+    return (uint32_t)(((uint64_t)r * n) >> 32);
+#endif
+}
+
+// binary search for `key` in sorted a[0..len)
+__device__ static inline bool contains_sorted(const int32_t *__restrict__ a, int len, int32_t key) {
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        int32_t v = __ldg(a + mid);
+        if (v < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < len && __ldg(a + lo) == key;
+}
+
+}  // namespace eb

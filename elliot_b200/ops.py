@@ -1,0 +1,178 @@
+"""Torch-tensor wrappers over the C ABI.  Torch is plumbing only (device memory, streams);
+all arithmetic happens in elliot_b200/csrc/*.cu.  Every op raises if its tensors are not on a
+CUDA device — there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+F32_STRIDES = (8, 16, 32, 64, 128, 256)
+
+
+def padded_dim(d):
+    """Row stride (in elements) the fp32 kernels need for `d` factors."""
+    for s in F32_STRIDES:
+        if d <= s:
+            return s
+    raise ValueError(f"factors={d} > 256 is not supported by the fp32 kernels")
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("elliot_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _chk_idx(*ts):
+    for t in ts:
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise TypeError("index tensors must be contiguous int32")
+
+
+def device_info():
+    sm = ctypes.c_int(0); cc = ctypes.c_int(0)
+    check(lib().eb_device_info(ctypes.byref(sm), ctypes.byref(cc)))
+    return sm.value, cc.value
+
+
+def bpr_step_f32(U, V, b, d, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None, racy=False):
+    """Throughput-mode BPR step on materialised triples (BPRMF_model.py:87-117 semantics)."""
+    _need_cuda(U, V, b, tu, ti, tj, loss)
+    _chk_idx(tu, ti, tj)
+    assert U.dtype == torch.float32 and V.dtype == torch.float32 and b.dtype == torch.float32
+    assert U.stride(1) == 1 and V.stride(1) == 1 and U.stride(0) == V.stride(0)
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), _ptr(tu), _ptr(ti), _ptr(tj), tu.numel(),
+                                    lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), 1 if racy else 0, _stream(U)))
+
+
+def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u, reg_b, reg_pos,
+                         reg_neg, loss=None, out=None, racy=False):
+    """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream)."""
+    _need_cuda(U, V, b, indptr, indices, loss)
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+    ou = oi = oj = None
+    if out is not None:
+        ou, oi, oj = out
+        _need_cuda(ou, oi, oj); _chk_idx(ou, oi, oj)
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_sampled_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), n_users, n_items, _ptr(indptr),
+                                            _ptr(indices), n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg,
+                                            _ptr(loss), _ptr(ou), _ptr(oi), _ptr(oj), 1 if racy else 0, _stream(U)))
+
+
+def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0):
+    _need_cuda(indptr, indices)
+    dev = indptr.device
+    u = torch.empty(n, dtype=torch.int32, device=dev); i = torch.empty_like(u); j = torch.empty_like(u)
+    with torch.cuda.device(dev):
+        check(lib().eb_bpr_sample_philox(n_users, n_items, _ptr(indptr), _ptr(indices), n, seed, first, _ptr(u),
+                                         _ptr(i), _ptr(j), _stream(indptr)))
+    return u, i, j
+
+
+def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, reg_pos, reg_neg, staging, loss_dev,
+                      loss_host, racy=False):
+    """End-to-end step from HOST (pinned) int32 triples; returns after the loss is back on the host."""
+    _need_cuda(U, V, b, staging, loss_dev)
+    n = tu_host.numel()
+    assert not tu_host.is_cuda and tu_host.dtype == torch.int32 and staging.numel() >= 3 * n
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_host_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), _ptr(tu_host), _ptr(ti_host),
+                                         _ptr(tj_host), n, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(staging),
+                                         _ptr(loss_dev), _ptr(loss_host), 1 if racy else 0, _stream(U)))
+
+
+class _Workspace:
+    """Grow-only device scratch buffer (the C ABI never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_ws_exact, _ws_sampler, _ws_score = _Workspace(), _Workspace(), _Workspace()
+
+
+def bpr_exact_f64(U, V, b, d, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None):
+    """Exact-mode step: identical to applying the triples one by one in order (BPRMF.py:119-127)."""
+    _need_cuda(U, V, b, tu, ti, tj, loss)
+    _chk_idx(tu, ti, tj)
+    assert U.dtype == torch.float64 and V.dtype == torch.float64 and b.dtype == torch.float64
+    n = tu.numel()
+    nu, ni = U.shape[0], V.shape[0]
+    nbytes = lib().eb_bpr_exact_workspace_bytes(n, nu, ni)
+    ws = _ws_exact.get(nbytes, U.device)
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_exact_f64(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), nu, ni, _ptr(tu), _ptr(ti), _ptr(tj), n,
+                                     lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), _ptr(ws), ws.numel(), _stream(U)))
+
+
+class MtSampler:
+    """Device replay of the reference sampler stream (custom_sampler.py:14-46).
+
+    indptr/set_indices: the reference's `_ui_dict` in list(set(...)) order; sorted_indices: same
+    CSR with rows sorted.  The MT19937 state persists across step() calls like the reference's
+    global np.random state does across epochs.
+    """
+
+    def __init__(self, n_users, n_items, indptr, set_indices, sorted_indices, seed=42):
+        _need_cuda(indptr, set_indices, sorted_indices)
+        assert indptr.dtype == torch.int64 and set_indices.dtype == torch.int32 and sorted_indices.dtype == torch.int32
+        self.n_users, self.n_items = n_users, n_items
+        self.indptr, self.set_indices, self.sorted_indices = indptr, set_indices, sorted_indices
+        self.state = torch.empty(625, dtype=torch.int32, device=indptr.device)
+        with torch.cuda.device(indptr.device):
+            check(lib().eb_mt_seed(_ptr(self.state), seed, _stream(indptr)))
+
+    def raw(self, n):
+        out = torch.empty(n, dtype=torch.int32, device=self.state.device)
+        with torch.cuda.device(self.state.device):
+            check(lib().eb_mt_raw(_ptr(self.state), _ptr(out), n, _stream(out)))
+        return out
+
+    def step(self, events):
+        dev = self.state.device
+        u = torch.empty(events, dtype=torch.int32, device=dev); i = torch.empty_like(u); j = torch.empty_like(u)
+        ws = _ws_sampler.get(lib().eb_mt_sampler_workspace_bytes(events), dev)
+        with torch.cuda.device(dev):
+            check(lib().eb_mt_sampler_step(_ptr(self.state), self.n_users, self.n_items, _ptr(self.indptr),
+                                           _ptr(self.set_indices), _ptr(self.sorted_indices), events, _ptr(u), _ptr(i),
+                                           _ptr(j), _ptr(ws), ws.numel(), _stream(u)))
+        return u, i, j
+
+
+def score_topk(U, V, bias, d, k, mask_indptr=None, mask_indices=None, users=None, user_begin=0, n_sel=None):
+    """Exact full-catalogue score + train mask + top-k (BPRMF_model.py:70-85 / BPRMF_batch_model.py:82-88)."""
+    _need_cuda(U, V, bias, mask_indptr, mask_indices, users)
+    if users is not None:
+        _chk_idx(users)
+        n_sel = users.numel()
+    elif n_sel is None:
+        n_sel = U.shape[0] - user_begin
+    n_items = V.shape[0]
+    dev = U.device
+    idx = torch.empty((n_sel, k), dtype=torch.int32, device=dev)
+    val = torch.empty((n_sel, k), dtype=U.dtype, device=dev)
+    esz = U.element_size()
+    ws = _ws_score.get(lib().eb_score_topk_workspace_bytes(n_sel, n_items, esz), dev)
+    fn = lib().eb_score_topk_f32 if U.dtype == torch.float32 else lib().eb_score_topk_f64
+    assert U.dtype in (torch.float32, torch.float64) and V.dtype == U.dtype
+    with torch.cuda.device(dev):
+        check(fn(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr), _ptr(mask_indices),
+                 _ptr(users), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(ws), ws.numel(), _stream(U)))
+    return idx, val

@@ -1,0 +1,149 @@
+/*
+ * elliot_b200.h — C ABI of the B200-native embedding-training core.
+ *
+ * The reference (sisinflab/elliot v0.3.1) is pure Python and has no FFI of its
+ * own; its hot path lives in per-model Python classes.  Every entry point below
+ * replaces the arithmetic of one reference function (cited per function,
+ * paths relative to the upstream tree) and is what the host-side plugin classes
+ * in elliot_b200/recommender/ bind through ctypes (see INTEGRATION.md for the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host / says host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - tables are row-major, row stride `ld` elements (ld >= d, ld % 4 == 0 for
+ *     the f32 kernels, padding columns must be zero and stay zero);
+ *   - ids are PRIVATE indices (dataset.py:211-217), int32;
+ *   - the library never allocates or frees caller-visible memory: scratch is
+ *     passed in, sized by the matching *_workspace_bytes() call;
+ *   - every function returns 0 on success, a negative EB_* code otherwise;
+ *     eb_last_error() gives the message for the calling thread.
+ *   - no CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef ELLIOT_B200_H
+#define ELLIOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB_OK 0
+#define EB_ERR_ARG (-1)      /* bad argument (shape, alignment, null) */
+#define EB_ERR_CUDA (-2)     /* CUDA runtime error */
+#define EB_ERR_WORKSPACE (-3)/* workspace too small */
+#define EB_ERR_DATA (-4)     /* data the reference itself cannot handle (e.g. a user owning every item) */
+
+const char *eb_last_error(void);
+int eb_version(void);
+/* number of SMs / compute capability major*10+minor of the current device */
+int eb_device_info(int *sm_count, int *cc);
+
+/* ------------------------------------------------------------------------
+ * BPR-MF training step.
+ * Replaces MFModel.train_step/update_factors
+ *   (elliot/recommender/latent_factor_models/BPRMF/BPRMF_model.py:87-117):
+ *   x_uk = b_k + U[u].V[k];  z = 1/(1+exp(x_ui-x_uj));
+ *   b_i += lr(z - reg_b b_i); b_j += lr(-z - reg_b b_j);
+ *   U[u] += lr((V_i-V_j) z - reg_u U[u]);
+ *   V_i += lr(U'[u] z - reg_pos V_i); V_j += lr(-U'[u] z - reg_neg V_j)
+ *   with U' the ALREADY UPDATED user row (the reference's view-aliasing).
+ * ------------------------------------------------------------------------ */
+
+/* Throughput mode: fp32, one launch over n materialised triples, rows updated
+ * with 128-bit vector atomics (Hogwild: reads within a launch may be stale).
+ * loss (optional, device double[1]) += sum softplus(-(x_ui-x_uj)).
+ * flags: bit0 = plain stores instead of atomics (racy Hogwild). */
+int eb_bpr_step_f32(float *U, float *V, float *item_bias, int d, int ld,
+                    const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                    float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
+                    double *loss, int flags, void *stream);
+
+/* Throughput mode with the sampler fused in: replaces Sampler.step/sample()
+ * (elliot/dataset/samplers/custom_sampler.py:24-46) by a counter-based device
+ * sampler with the same distribution (u uniform over users, i uniform over
+ * u's train items, j uniform over items not in u's train set, by rejection)
+ * but a different stream (Philox4x32-10 keyed by seed, counter = triple index
+ * `first_triple`+t), then applies the update above.  csr_indices rows must be
+ * sorted ascending.  out_u/out_i/out_j (optional) receive the sampled triples. */
+int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int d, int ld,
+                            int32_t n_users, int32_t n_items,
+                            const int64_t *csr_indptr, const int32_t *csr_indices,
+                            int64_t n, uint64_t seed, uint64_t first_triple,
+                            float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
+                            double *loss, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                            int flags, void *stream);
+
+/* Sample only (no update): same sampler as above, for tests and for host
+ * pipelines that want materialised triples. */
+int eb_bpr_sample_philox(int32_t n_users, int32_t n_items,
+                         const int64_t *csr_indptr, const int32_t *csr_indices,
+                         int64_t n, uint64_t seed, uint64_t first_triple,
+                         int32_t *out_u, int32_t *out_i, int32_t *out_j, void *stream);
+
+/* End-to-end variant of eb_bpr_step_f32 for HOST triples: copies the three
+ * host index arrays into `staging` (device, 3*n int32), runs the step, copies
+ * the loss back into *loss_host and synchronises the stream. */
+int eb_bpr_step_host_f32(float *U, float *V, float *item_bias, int d, int ld,
+                         const int32_t *tu_host, const int32_t *ti_host, const int32_t *tj_host, int64_t n,
+                         float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
+                         int32_t *staging, double *loss_dev, double *loss_host, int flags, void *stream);
+
+/* Exact mode: fp64, result identical to applying the n triples strictly one
+ * after the other in array order (what the reference does with batch_size
+ * forced to 1, BPRMF.py:80,119-127).  Row-level turn counters serialise only
+ * the triples that really conflict.  n_users/n_items size the counters. */
+size_t eb_bpr_exact_workspace_bytes(int64_t n, int32_t n_users, int32_t n_items);
+int eb_bpr_exact_f64(double *U, double *V, double *item_bias, int d, int ld,
+                     int32_t n_users, int32_t n_items,
+                     const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                     double lr, double reg_u, double reg_b, double reg_pos, double reg_neg,
+                     double *loss, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Exact replay of the reference sampler's random stream on the device.
+ * Replaces Sampler.__init__/step (custom_sampler.py:14-46): legacy
+ * np.random.seed(42) MT19937, randint() = 32-bit masked rejection, no draw
+ * when the range is 1.  `state` is 625 uint32 (624 words + position) on the
+ * device; it advances by exactly the draws the reference would consume, so
+ * consecutive calls continue one stream across epochs as the reference does.
+ * set_indices rows are in the reference's list(set(...)) order
+ * (custom_sampler.py:21); sorted_indices is the same CSR with rows sorted
+ * (membership tests).  Returns EB_ERR_DATA if a sampled user owns every item
+ * (the reference never terminates there).
+ * ------------------------------------------------------------------------ */
+int eb_mt_seed(uint32_t *state, uint32_t seed, void *stream);
+size_t eb_mt_sampler_workspace_bytes(int64_t events);
+int eb_mt_sampler_step(uint32_t *state, int32_t n_users, int32_t n_items,
+                       const int64_t *indptr, const int32_t *set_indices, const int32_t *sorted_indices,
+                       int64_t events, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* raw tempered 32-bit outputs (testing the generator against numpy) */
+int eb_mt_raw(uint32_t *state, uint32_t *out, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Full-catalogue scoring + train-item mask + per-user top-k.
+ * Replaces MFModel.get_user_predictions (BPRMF_model.py:70-85) and
+ * BPRMF_batch_model.predict/get_top_k (BPRMF_batch_model.py:82-88):
+ *   s = bias + U[u] @ V.T;  s[train items of u] = -inf;  top-k, descending,
+ *   ties -> lower item index first (tf.nn.top_k rule).
+ * users: optional list of n_sel private user ids (NULL = user_begin..+n_sel).
+ * mask CSR rows = train items per user (NULL = no mask).  Slots with no
+ * finite candidate get idx -1 / val -inf.
+ * ------------------------------------------------------------------------ */
+size_t eb_score_topk_workspace_bytes(int64_t n_sel, int32_t n_items, int elem_size);
+int eb_score_topk_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
+                      const int64_t *mask_indptr, const int32_t *mask_indices,
+                      const int32_t *users, int32_t user_begin, int64_t n_sel, int k,
+                      int32_t *out_idx, float *out_val, void *workspace, size_t workspace_bytes, void *stream);
+int eb_score_topk_f64(const double *U, const double *V, const double *item_bias, int32_t n_items, int d, int ld,
+                      const int64_t *mask_indptr, const int32_t *mask_indices,
+                      const int32_t *users, int32_t user_begin, int64_t n_sel, int k,
+                      int32_t *out_idx, double *out_val, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
