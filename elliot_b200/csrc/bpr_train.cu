@@ -271,22 +271,27 @@ __global__ void __launch_bounds__(128) bpr_exact_kernel(const ExactParams p) {
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= p.n) break;
         const int u = __ldg(p.tu + t), i = __ldg(p.ti + t), j = __ldg(p.tj + t);
-        int32_t *cnt = nullptr;
-        int want = 0;
-        if (lane == 0) { cnt = p.cntU + u; want = __ldg(p.ku + t); }
-        else if (lane == 1) { cnt = p.cntI + i; want = __ldg(p.ki + t); }
-        else if (lane == 2) { cnt = p.cntI + j; want = __ldg(p.kj + t); }
-        if (lane < 3) {
+        const int wu = __ldg(p.ku + t), wi = __ldg(p.ki + t), wj = __ldg(p.kj + t);
+        int32_t *cu = p.cntU + u, *ci = p.cntI + i, *cj = p.cntI + j;
+        // Every lane performs the three acquire loads itself and the exit decision is a
+        // warp vote: control flow stays warp-uniform and each lane's later row loads are
+        // ordered after ITS OWN acquires (no reliance on cross-lane ordering).
+        {
             unsigned ns = 8;
-            while (ld_acquire(cnt) != want) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
+            for (;;) {
+                const bool ready = (ld_acquire(cu) == wu) & (ld_acquire(ci) == wi) & (ld_acquire(cj) == wj);
+                if (__all_sync(0xffffffffu, ready)) break;
+                __nanosleep(ns);
+                if (ns < 128) ns <<= 1;
+            }
         }
-        __syncwarp();
         double *pu = p.U + (int64_t)u * p.ld, *pi = p.V + (int64_t)i * p.ld, *pj = p.V + (int64_t)j * p.ld;
         double a[NE], vi[NE], vj[NE];
         double xi = 0.0, xj = 0.0;
 #pragma unroll
         for (int e = 0; e < NE; e++) {
             const int k = lane + 32 * e;
+            a[e] = 0.0; vi[e] = 0.0; vj[e] = 0.0;
             if (k < p.d) {
                 a[e] = __ldcg(pu + k); vi[e] = __ldcg(pi + k); vj[e] = __ldcg(pj + k);
                 xi = __dadd_rn(xi, __dmul_rn(a[e], vi[e]));
@@ -303,28 +308,32 @@ __global__ void __launch_bounds__(128) bpr_exact_kernel(const ExactParams p) {
         xj = __dadd_rn(xj, bj);
         const double x = __dadd_rn(xi, -xj);
         const double z = 1.0 / (1.0 + exp(x));  // BPRMF_model.py:98
-        if (lane == 0) loss_acc += (x > 0) ? log1p(exp(-x)) : (-x + log1p(exp(x)));
+        const double sp = (x > 0) ? log1p(exp(-x)) : (-x + log1p(exp(x)));   // all lanes: no divergence
+        loss_acc += (lane == 0) ? sp : 0.0;
 #pragma unroll
         for (int e = 0; e < NE; e++) {
             const int k = lane + 32 * e;
-            if (k < p.d) {
-                // d_u = (V_i - V_j) z - reg_u U[u];  U[u] += lr d_u   (BPRMF_model.py:108-109)
-                const double un = __dadd_rn(
-                    a[e], __dmul_rn(p.lr, __dadd_rn(__dmul_rn(__dadd_rn(vi[e], -vj[e]), z), -__dmul_rn(p.reg_u, a[e]))));
-                // d_i = U'[u] z - reg_pos V_i (BPRMF_model.py:112-113), d_j = -U'[u] z - reg_neg V_j (:116-117)
-                const double uz = __dmul_rn(un, z);
-                const double in_ = __dadd_rn(vi[e], __dmul_rn(p.lr, __dadd_rn(uz, -__dmul_rn(p.reg_pos, vi[e]))));
-                const double jn = __dadd_rn(vj[e], __dmul_rn(p.lr, __dadd_rn(-uz, -__dmul_rn(p.reg_neg, vj[e]))));
-                __stcg(pu + k, un); __stcg(pi + k, in_); __stcg(pj + k, jn);
-            }
+            // d_u = (V_i - V_j) z - reg_u U[u];  U[u] += lr d_u   (BPRMF_model.py:108-109)
+            const double un = __dadd_rn(
+                a[e], __dmul_rn(p.lr, __dadd_rn(__dmul_rn(__dadd_rn(vi[e], -vj[e]), z), -__dmul_rn(p.reg_u, a[e]))));
+            // d_i = U'[u] z - reg_pos V_i (BPRMF_model.py:112-113), d_j = -U'[u] z - reg_neg V_j (:116-117)
+            const double uz = __dmul_rn(un, z);
+            const double in_ = __dadd_rn(vi[e], __dmul_rn(p.lr, __dadd_rn(uz, -__dmul_rn(p.reg_pos, vi[e]))));
+            const double jn = __dadd_rn(vj[e], __dmul_rn(p.lr, __dadd_rn(-uz, -__dmul_rn(p.reg_neg, vj[e]))));
+            if (k < p.d) { __stcg(pu + k, un); __stcg(pi + k, in_); __stcg(pj + k, jn); }
         }
-        if (lane == 0) {
-            __stcg(p.b + i, __dadd_rn(bi, __dmul_rn(p.lr, __dadd_rn(z, -__dmul_rn(p.reg_b, bi)))));
-            __stcg(p.b + j, __dadd_rn(bj, __dmul_rn(p.lr, __dadd_rn(-z, -__dmul_rn(p.reg_b, bj)))));
-        }
+        const double bin = __dadd_rn(bi, __dmul_rn(p.lr, __dadd_rn(z, -__dmul_rn(p.reg_b, bi))));
+        const double bjn = __dadd_rn(bj, __dmul_rn(p.lr, __dadd_rn(-z, -__dmul_rn(p.reg_b, bj))));
+        if (lane == 0) { __stcg(p.b + i, bin); __stcg(p.b + j, bjn); }
         __threadfence();
-        __syncwarp();
-        if (lane < 3) st_release(cnt, want + 1);
+        // the release stores depend on a full-warp vote that every lane reaches only after
+        // its own fence: all 32 lanes' row stores are visible before any counter moves
+        const unsigned done = __ballot_sync(0xffffffffu, true);
+        if (done == 0xffffffffu) {
+            if (lane == 0) st_release(cu, wu + 1);
+            else if (lane == 1) st_release(ci, wi + 1);
+            else if (lane == 2) st_release(cj, wj + 1);
+        }
     }
     if (p.loss && lane == 0 && loss_acc != 0.0) atomicAdd(p.loss, loss_acc);
 }
