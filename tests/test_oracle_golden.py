@@ -75,3 +75,22 @@ def test_sampler_rejects_user_owning_everything():
     indptr = np.array([0, 3], np.int64); indices = np.array([0, 1, 2], np.int32)
     with pytest.raises(RuntimeError):
         oracle.sampler_step(oracle.Rng(42), 1, 3, indptr, indices, 5)
+
+
+def test_numpy_port_matches_golden(golden_tiny):
+    """The interpreter-bound NumPy port used as the reference-speed CPU baseline replays the
+    reference's stream and tables exactly."""
+    from oracle import bprmf_numpy as bn
+    g = golden_tiny
+    rows = [list(g["ui_indices"][g["ui_indptr"][u]:g["ui_indptr"][u + 1]]) for u in range(len(g["users"]))]
+    m = bn.SequentialBPR(len(g["users"]), len(g["items"]), int(g["d"]), *[float(x) for x in g["hp"]],
+                         seed=int(g["model_seed"]))
+    assert np.array_equal(m.P, g["U0"])
+    np.random.seed(42)
+    T = int(g["transactions"])
+    got = []
+    for u, i, j in bn.triple_stream(rows, len(g["items"]), T):
+        got.append((u, i, j)); m.sgd(u, i, j)
+    got = np.array(got)
+    assert np.array_equal(got[:, 0], g["tu"][:T]) and np.array_equal(got[:, 1], g["ti"][:T]) and np.array_equal(got[:, 2], g["tj"][:T])
+    assert np.abs(m.P - g["U_ep1"]).max() < 1e-13 and np.abs(m.Q - g["V_ep1"]).max() < 1e-13
