@@ -1,0 +1,84 @@
+"""Minimal evaluator for the host mirror: nDCG / HR / Precision / Recall with the reference's
+definitions (elliot/evaluation/evaluator.py:79-147; ndcg.py:68-125; relevance.py:55,80-82;
+hit_rate.py, precision.py, recall.py), vectorised over (users x k) index arrays.
+
+The reference Evaluator is the parity judge and is NOT re-implemented in breadth (SURVEY.md §2
+#23 out of scope): tests/test_host_parity.py checks these four against numbers the reference's
+own Evaluator produced on the same lists (tests/golden)."""
+import math
+
+import numpy as np
+
+SUPPORTED = {"ndcg": "nDCG", "hr": "HR", "precision": "Precision", "recall": "Recall"}
+
+
+class Evaluator:
+    def __init__(self, data, params):
+        self._data, self._params = data, params
+        ev = data.config.evaluation
+        self._k = getattr(ev, "cutoffs", [data.config.top_k])
+        self._k = self._k if isinstance(self._k, list) else [self._k]
+        if any(np.array(self._k) > data.config.top_k):
+            raise Exception("Cutoff values must be smaller than recommendation list length (top_k)")
+        self._metrics = []
+        for m in ev.simple_metrics:
+            if m.lower() not in SUPPORTED:
+                raise Exception(f"metric {m} is not available in elliot_b200's evaluator "
+                                f"(use the reference Evaluator through ProxyRecommender for the other 40)")
+            self._metrics.append(SUPPORTED[m.lower()])
+        self._sets = {"test": data.eval_csr("test"), "val": data.eval_csr("val")}
+
+    def get_needed_recommendations(self):
+        return self._data.config.top_k
+
+    # recommendations: (val, test) pair of {public_user: [(public_item, score), ...]}
+    def eval(self, recommendations):
+        out = {}
+        for k in self._k:
+            res = {}
+            for slot, which in ((0, "val"), (1, "test")):
+                cs = self._sets[which]
+                res[which] = None if cs is None else self._eval_dict(recommendations[slot], cs, k)
+            if res["val"] is None:
+                res["val"] = res["test"]
+            if res["test"] is None:
+                res["test"] = res["val"]
+            out[k] = {"val_results": res["val"], "val_statistical_results": {},
+                      "test_results": res["test"], "test_statistical_results": {}}
+        return out
+
+    def _eval_dict(self, recs, cs, k):
+        pub_u, pub_i = self._data.public_users, self._data.public_items
+        users = [u for u in recs if u in pub_u]
+        idx = np.full((len(users), k), -1, np.int64)
+        for r, u in enumerate(users):
+            row = [pub_i.get(it, -1) for it, _ in recs[u][:k]]
+            idx[r, :len(row)] = row
+        return self.eval_arrays(np.array([pub_u[u] for u in users], np.int64), idx, cs, k)
+
+    def eval_arrays(self, priv_users, idx, cs, k):
+        """idx: (n, >=k) private item ids (−1 = empty slot), rows aligned with priv_users."""
+        indptr, rel_idx, rel_gain = cs
+        disc = np.array([math.log(2) / math.log(r + 2) for r in range(k)])      # relevance.py:55
+        acc = {m: [] for m in self._metrics}
+        for row, pu in zip(idx[:, :k], priv_users):
+            lo, hi = indptr[pu], indptr[pu + 1]
+            if hi == lo:                       # users without relevant test items are skipped
+                continue
+            gains = dict(zip(rel_idx[lo:hi].tolist(), rel_gain[lo:hi].tolist()))
+            g = np.array([gains.get(int(it), 0.0) if it >= 0 else 0.0 for it in row])
+            hits = g > 0
+            if "nDCG" in acc:
+                ideal = np.sort(rel_gain[lo:hi])[::-1][:k]
+                idcg = float((ideal * disc[:len(ideal)]).sum())
+                dcg = float((g * disc[:len(g)]).sum())
+                acc["nDCG"].append(dcg / idcg if dcg > 0 else 0.0)
+            if "HR" in acc:
+                acc["HR"].append(1.0 if hits.any() else 0.0)
+            # Precision/Recall sum the DISCOUNTED-relevance lookups? No: binary relevance
+            # (precision.py / recall.py use relevance.binary_relevance.get_rel -> 1/0).
+            if "Precision" in acc:
+                acc["Precision"].append(hits.sum() / k)
+            if "Recall" in acc:
+                acc["Recall"].append(hits.sum() / (hi - lo))
+        return {m: (float(np.mean(v)) if v else 0.0) for m, v in acc.items()}

@@ -1,0 +1,3 @@
+"""Model registry: the class names the reference resolves from the YAML model key
+(elliot/run.py:75, elliot/recommender/__init__.py)."""
+from .bprmf import BPRMF, MFModel  # noqa: F401

@@ -142,6 +142,27 @@ def make_case(name, n_users, n_items, mean_pos, d, seed_data, model_seed, epochs
     print(name, "users", len(users), "items", len(items), "T", T, "triples", len(tu), {m: round(v, 6) for m, v in metrics.items()})
 
 
+def make_split_case():
+    """Reference Splitter (base_splitter.py:62-111,256-274) on a small frame: pins the split stream."""
+    sys.path.insert(0, REF)
+    from elliot.splitter.base_splitter import Splitter
+    g = np.random.default_rng(5)
+    rows = []
+    for u in g.permutation(40):
+        for it in g.choice(60, size=int(g.integers(3, 15)), replace=False):
+            rows.append((int(u) * 2 + 1, int(it) + 500, 1.0))
+    rows = np.array(rows)
+    g.shuffle(rows)
+    df = pd.DataFrame({"userId": rows[:, 0].astype(np.int64), "itemId": rows[:, 1].astype(np.int64), "rating": rows[:, 2]})
+    ns = SimpleNamespace(test_splitting=SimpleNamespace(strategy="random_subsampling", test_ratio=0.2))
+    (train, test), = Splitter(df.copy(), ns, 42).process_splitting()
+    np.savez_compressed(os.path.join(OUT, "split_random_subsampling.npz"), data=rows,
+                        train=train[["userId", "itemId", "rating"]].to_numpy(),
+                        test=test[["userId", "itemId", "rating"]].to_numpy())
+    print("split", len(df), len(train), len(test))
+
+
 if __name__ == "__main__":
+    make_split_case()
     make_case("tiny", n_users=60, n_items=48, mean_pos=8, d=10, seed_data=1, model_seed=42, epochs=2, k=10)
     make_case("small", n_users=400, n_items=300, mean_pos=20, d=64, seed_data=2, model_seed=7, epochs=2, k=10)

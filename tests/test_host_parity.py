@@ -1,0 +1,99 @@
+"""CPU tests of the host-side mirror against goldens minted from the reference's own DataSet,
+Splitter, Sampler and Evaluator (oracle/gen_golden.py)."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from elliot_b200.dataset import DataSet
+from elliot_b200.evaluation import Evaluator
+from elliot_b200.recommender.early_stopping import EarlyStopping
+from elliot_b200.run import split_random_subsampling
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _frames(g):
+    f = lambda a: pd.DataFrame({"userId": a[:, 0].astype(np.int64), "itemId": a[:, 1].astype(np.int64), "rating": a[:, 2]})
+    return f(g["train"]), f(g["test"])
+
+
+def _config(k):
+    return SimpleNamespace(config_test=False, top_k=k,
+                           evaluation=SimpleNamespace(simple_metrics=["nDCG", "HR", "Precision", "Recall"],
+                                                      relevance_threshold=0, paired_ttest=False, cutoffs=[k]))
+
+
+def test_dataset_id_order_and_sampler_rows_match_reference(golden):
+    g = golden
+    data = DataSet(_config(int(g["k"])), _frames(g))
+    assert data.users == list(g["users"]) and data.items == list(g["items"])        # dataset.py:201-202 ordering
+    assert data.transactions == int(g["transactions"])
+    rows = data.sampler_rows()                                                        # custom_sampler.py:21 ordering
+    flat = np.array([x for r in rows for x in r], np.int32)
+    assert np.array_equal(flat, g["ui_indices"])
+    assert np.array_equal(np.cumsum([0] + [len(r) for r in rows]), g["ui_indptr"])
+    assert data.sp_i_train.nnz == data.transactions and data.allunrated_mask.shape == (data.num_users, data.num_items)
+    assert (~data.allunrated_mask).sum() == data.transactions
+
+
+def test_evaluator_matches_reference_metrics(golden):
+    """nDCG/HR/Precision/Recall on the reference's own top-k lists == reference Evaluator output."""
+    g = golden
+    k = int(g["k"])
+    data = DataSet(_config(k), _frames(g))
+    ev = Evaluator(data, SimpleNamespace(meta=SimpleNamespace()))
+    recs = {}
+    for pu, u in enumerate(data.users):
+        recs[u] = [(data.items[i], float(v)) for i, v in zip(g["rec_idx"][pu], g["rec_val"][pu]) if i >= 0]
+    got = ev.eval((recs, recs))[k]["test_results"]
+    want = dict(zip(g["metric_names"].tolist(), g["metric_vals"].tolist()))
+    for m in want:
+        assert abs(got[m] - want[m]) < 1e-12, (m, got[m], want[m])
+
+
+def test_random_subsampling_split_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "split_random_subsampling.npz"))
+    a = g["data"]
+    df = pd.DataFrame({"userId": a[:, 0].astype(np.int64), "itemId": a[:, 1].astype(np.int64), "rating": a[:, 2]})
+    (train, test), = split_random_subsampling(df, 0.2, 42)
+    assert np.array_equal(train[["userId", "itemId", "rating"]].to_numpy(), g["train"])
+    assert np.array_equal(test[["userId", "itemId", "rating"]].to_numpy(), g["test"])
+
+
+def test_early_stopping_rules():
+    mk = lambda **kw: EarlyStopping(SimpleNamespace(**kw), "nDCG", 10, [10], ["nDCG"])
+    res = lambda vals: [{10: {"val_results": {"nDCG": v}}} for v in vals]
+    assert not mk().stop([], res([0.1, 0.05]))                       # inactive without options
+    es = mk(patience=1)
+    assert not es.stop([], res([0.1]))
+    assert not es.stop([], res([0.1, 0.2]))                          # still improving
+    assert es.stop([], res([0.3, 0.2, 0.1]))                         # two consecutive drops
+    assert not es.stop([], res([0.3, 0.1, 0.2]))
+    assert not mk(patience=0).stop([], res([0.3, 0.2, 0.1]))         # reference quirk: a 1-value window has no pair
+    el = mk(patience=1, monitor="loss")
+    assert el.stop([1.0, 2.0], []) and not el.stop([2.0, 1.0], [])
+    em = mk(patience=1, min_delta=0.05)
+    assert em.stop([], res([0.10, 0.12]))                            # improvement below min_delta counts as stall
+    with pytest.raises(Exception):
+        mk(monitor="MAP")
+
+
+def test_base_model_contract_errors():
+    from elliot_b200.recommender.base_recommender_model import BaseRecommenderModel
+
+    class M(BaseRecommenderModel):
+        train = get_recommendations = get_loss = get_params = get_results = lambda self, *a: None
+
+    g = dict(np.load(os.path.join(GOLDEN, "bprmf_tiny.npz")))
+    data = DataSet(_config(10), _frames(g))
+    with pytest.raises(Exception):
+        M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(validation_metric="MAP@10")))
+    with pytest.raises(Exception):
+        M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(validation_metric="nDCG@5")))
+    with pytest.raises(Exception):
+        M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(validation_rate=5), epochs=2))
+    m = M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(), epochs=3, seed=7))
+    assert m.get_base_params_shortcut() == "seed=7_e=3_bs=-1"
