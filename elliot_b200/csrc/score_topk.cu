@@ -21,6 +21,7 @@ struct ScoreParams {
     const int64_t *mask_indptr;
     const int32_t *mask_indices;
     const int32_t *users;
+    const int32_t *positions;  // optional: row q works on user_begin+positions[q] and writes output row positions[q]
     int32_t user_begin;
     int64_t n_sel;
     int k;
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(const ScoreParams
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *s = p.scratch + (int64_t)blockIdx.x * p.n_items;
     for (int64_t q = blockIdx.x; q < p.n_sel; q += gridDim.x) {
-        const int u = p.users ? p.users[q] : p.user_begin + (int)q;
+        const int64_t qo = p.positions ? (int64_t)p.positions[q] : q;
+        const int u = p.users ? p.users[q] : p.user_begin + (int)qo;
         __syncthreads();
         for (int k = threadIdx.x; k < p.d; k += blockDim.x) su[k] = p.U[(int64_t)u * p.ld + k];
         __syncthreads();
@@ -95,8 +97,8 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(const ScoreParams
                 }
                 if (lane == 0) {
                     const bool ok = bv > neg_inf<T>();
-                    p.out_idx[q * p.k + r] = ok ? bi : -1;
-                    p.out_val[q * p.k + r] = bv;
+                    p.out_idx[qo * p.k + r] = ok ? bi : -1;
+                    p.out_val[qo * p.k + r] = bv;
                     win_i = ok ? bi : -1;
                     if (ok) s[bi] = neg_inf<T>();
                 }
@@ -104,8 +106,8 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(const ScoreParams
             __syncthreads();
             if (win_i < 0) {  // nothing finite left: pad the tail
                 for (int rr = r + 1 + threadIdx.x; rr < p.k; rr += blockDim.x) {
-                    p.out_idx[q * p.k + rr] = -1;
-                    p.out_val[q * p.k + rr] = neg_inf<T>();
+                    p.out_idx[qo * p.k + rr] = -1;
+                    p.out_val[qo * p.k + rr] = neg_inf<T>();
                 }
                 break;
             }
@@ -122,7 +124,7 @@ template <typename T>
 static int score_topk_exact(const T *U, const T *V, const T *bias, int32_t n_items, int d, int ld,
                             const int64_t *mask_indptr, const int32_t *mask_indices, const int32_t *users,
                             int32_t user_begin, int64_t n_sel, int k, int32_t *out_idx, T *out_val, void *workspace,
-                            size_t workspace_bytes, void *stream) {
+                            size_t workspace_bytes, void *stream, const int32_t *positions = nullptr) {
     EB_ARG(U && V && out_idx && out_val, "null pointer");
     EB_ARG(d >= 1 && ld >= d && n_items >= 1 && k >= 1, "bad shape d=%d ld=%d n_items=%d k=%d", d, ld, n_items, k);
     EB_ARG((mask_indptr == nullptr) == (mask_indices == nullptr), "mask CSR: both or neither");
@@ -132,7 +134,7 @@ static int score_topk_exact(const T *U, const T *V, const T *bias, int32_t n_ite
     if (workspace_bytes < row || !workspace)
         return set_err(EB_ERR_WORKSPACE, "workspace %zu < one score row %zu", workspace_bytes, row);
     if ((size_t)ctas * row > workspace_bytes) ctas = (int64_t)(workspace_bytes / row);
-    ScoreParams<T> p{U, V, bias, n_items, d, ld, mask_indptr, mask_indices, users, user_begin, n_sel, k, out_idx, out_val,
+    ScoreParams<T> p{U, V, bias, n_items, d, ld, mask_indptr, mask_indices, users, positions, user_begin, n_sel, k, out_idx, out_val,
                      (T *)workspace};
     score_topk_exact_kernel<T><<<(unsigned)ctas, 256, sizeof(T) * (size_t)d, (cudaStream_t)stream>>>(p);
     EB_CUDA(cudaGetLastError());
@@ -159,4 +161,14 @@ extern "C" int eb_score_topk_f64(const double *U, const double *V, const double 
                                  void *workspace, size_t workspace_bytes, void *stream) {
     return eb::score_topk_exact<double>(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, users, user_begin,
                                         n_sel, k, out_idx, out_val, workspace, workspace_bytes, stream);
+}
+
+// re-check entry used by score_topk_tc.cu: row q scores user user_begin+positions[q] and writes output row positions[q]
+extern "C" int eb_score_topk_f32_mapped(const float *U, const float *V, const float *item_bias, int32_t n_items, int d,
+                                        int ld, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                        const int32_t *positions, int32_t user_begin, int64_t n_sel, int k,
+                                        int32_t *out_idx, float *out_val, void *workspace, size_t workspace_bytes,
+                                        void *stream) {
+    return eb::score_topk_exact<float>(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, nullptr, user_begin,
+                                       n_sel, k, out_idx, out_val, workspace, workspace_bytes, stream, positions);
 }

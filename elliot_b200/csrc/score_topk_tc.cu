@@ -1,0 +1,560 @@
+// score_topk_tc.cu — full-catalogue U·Vᵀ on the 5th-gen tensor cores (tcgen05 + TMEM + TMA)
+// with the per-user masked top-k fused into the epilogue and an exact fp32 re-rank.
+//
+// Replaces BPRMF_batch_model.predict/get_top_k (BPRMF_batch_model.py:82-88) /
+// MFModel.get_user_predictions (BPRMF_model.py:70-85) at catalogue scale: the (users x items)
+// score matrix is never materialised.
+//
+// Pipeline per CTA (persistent, one CTA per SM, 6 warps):
+//   warp 0   TMA producer : A tile (128 users x KP, bf16, once per user block) and a ring of
+//                           B tiles (BN items x KP) via cp.async.bulk.tensor, 128B swizzle
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                           (M=128, N=BN, K=16) into one of two TMEM accumulators (2 x BN cols)
+//   warps 2-5 epilogue    : thread r owns user row r: tcgen05.ld 32 columns at a time, a
+//                           running threshold filters all but the current top-KC approximate
+//                           scores (max-of-32 fast path), survivors are checked against the
+//                           train CSR and kept in a per-row candidate list in shared memory.
+// After the last item tile each warp re-scores its rows' KC=32 candidates EXACTLY in fp32
+// (same summation order as score_topk.cu), sorts them with a 32-lane bitonic network
+// (score desc, index asc) and certifies the result:
+//      every item not in the list has approx score <= tau (final threshold), so its exact
+//      score is <= tau + eps_u with eps_u = c * ||u|| * max_i ||v_i|| (bf16 rounding bound);
+//      if the k-th exact score exceeds tau + eps_u the list is provably the exact top-k.
+// Users that cannot be certified are appended to a list and re-done by the exact kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace eb {
+
+constexpr int TC_BM = 128;        // users per block (UMMA M)
+constexpr int TC_KC = 32;         // candidates kept per user (one per lane in the re-rank)
+constexpr int TC_THREADS = 192;   // 6 warps
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, one CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t gets row (quadrant*32 + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle (what TMA SWIZZLE_128B writes for
+// a {64 bf16, rows} box): rows are 128 B apart, 8-row groups 1024 B apart.
+// Field layout (cute::UMMA::SmemDescriptor): [0,14) addr>>4, [16,30) LBO>>4 (=1, unused for
+// swizzled K-major), [32,46) SBO>>4 (=64), [46,48) version=1, [61,64) layout=2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- parameters
+struct TcParams {
+    // exact-side inputs
+    const float *U, *V, *bias;   // fp32 tables (row stride ld), bias may be null
+    int d, ld;
+    int32_t n_items;
+    const int64_t *mask_indptr;
+    const int32_t *mask_indices; // sorted rows
+    int32_t user_begin;
+    int32_t n_sel;
+    int k;
+    // prepared by tc_prep kernels
+    const float *unorm;          // ||u|| per selected user
+    const float *vstat;          // [0] = max ||v||, [1] = max |bias|
+    const float *bmax_chunk;     // max bias per 32-item chunk (null if no bias)
+    // outputs
+    int32_t *out_idx;
+    float *out_val;
+    int32_t *flag_count;         // number of uncertified users
+    int32_t *flag_list;          // their positions q in [0, n_sel)
+    float *dump;                 // optional dense n_sel x n_items approximate scores (tests)
+    float eps_scale;             // c in eps_u = c * ||u|| * max||v|| + 1e-6 * (...)
+};
+
+template <int KP> struct TcCfg {
+    static constexpr int KB = KP / 64;                       // 64-wide K blocks (one swizzle atom each)
+    static constexpr int BN = KP <= 128 ? 256 : 128;         // items per tile (UMMA N)
+    static constexpr int STAGES = KP == 64 ? 3 : 2;
+    static constexpr int A_BYTES = TC_BM * KP * 2;
+    static constexpr int B_BYTES = BN * KP * 2;
+    static constexpr int CAND_BYTES = TC_BM * TC_KC * 8;
+    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + CAND_BYTES + 256;
+};
+
+__device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+template <int KP, bool DUMP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using C = TcCfg<KP>;
+    constexpr int KB = C::KB, BN = C::BN, S = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
+    uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
+    float *cval = reinterpret_cast<float *>(sB + S * C::B_BYTES);            // [KC][128]
+    int *cidx = reinterpret_cast<int *>(cval + TC_KC * TC_BM);               // [KC][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cidx + TC_KC * TC_BM);
+    // barrier indices
+    const uint32_t bar0 = smem_u32(bars);
+    auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(S + s); };
+    const uint32_t A_FULL = bar0 + 8u * (2 * S), A_EMPTY = bar0 + 8u * (2 * S + 1);
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * S + 2 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * S + 4 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (p.n_items + BN - 1) / BN;
+    const int n_mblocks = (p.n_sel + TC_BM - 1) / TC_BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0; uint32_t it = 0;
+            for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x, it++) {
+                mbar_wait(A_EMPTY, (it & 1) ^ 1);
+                mbar_expect_tx(A_FULL, C::A_BYTES);
+                for (int kb = 0; kb < KB; kb++)
+                    tma_load_2d(smem_u32(sA + kb * (TC_BM * 128)), &tmA, A_FULL, kb * 64, mb * TC_BM);
+                for (int t = 0; t < n_tiles; t++) {
+                    mbar_wait(B_EMPTY(s), ph ^ 1);
+                    mbar_expect_tx(B_FULL(s), C::B_BYTES);
+                    for (int kb = 0; kb < KB; kb++)
+                        tma_load_2d(smem_u32(sB + s * C::B_BYTES + kb * (BN * 128)), &tmB, B_FULL(s), kb * 64, t * BN);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+            int s = 0; uint32_t ph = 0; uint32_t it = 0; uint32_t tile = 0;
+            for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x, it++) {
+                mbar_wait(A_FULL, it & 1);
+                for (int t = 0; t < n_tiles; t++, tile++) {
+                    const int acc = tile & 1;
+                    mbar_wait(ACC_EMPTY(acc), ((tile >> 1) & 1) ^ 1);
+                    mbar_wait(B_FULL(s), ph);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+                    for (int kb = 0; kb < KB; kb++) {
+                        const uint32_t a_addr = smem_u32(sA + kb * (TC_BM * 128));
+                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + kb * (BN * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; k++)   // UMMA_K = 16 bf16 = 32 B inside the 128-B swizzle atom
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (kb | k) != 0);
+                    }
+                    umma_commit(B_EMPTY(s));          // B stage reusable once these MMAs retire
+                    umma_commit(ACC_FULL(acc));       // accumulator ready for the epilogue
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(A_EMPTY);                 // A reusable after the block's last MMA
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..5 =====================
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;             // row inside the 128-user block
+        const float NEG = -CUDART_INF_F;
+        uint32_t tile = 0;
+        for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x) {
+            const int q = mb * TC_BM + row;           // position in the selected user range
+            const bool valid = q < p.n_sel;
+            const int u = p.user_begin + (valid ? q : 0);
+            const int32_t *mrow = nullptr; int mlen = 0;
+            if (valid && p.mask_indptr) {
+                const int64_t b0 = p.mask_indptr[u];
+                mrow = p.mask_indices + b0; mlen = (int)(p.mask_indptr[u + 1] - b0);
+            }
+            int count = 0, minslot = 0;
+            float thresh = NEG;                       // min of the kept set once it is full
+
+            auto try_insert = [&](float s, int col) {
+                if (col >= p.n_items) return;         // TMA zero-filled rows past the catalogue
+                if (mrow && contains_sorted(mrow, mlen, col)) return;   // train item -> -inf
+                if (count < TC_KC) {
+                    cval[count * TC_BM + row] = s; cidx[count * TC_BM + row] = col; count++;
+                    if (count < TC_KC) return;
+                } else {
+                    cval[minslot * TC_BM + row] = s; cidx[minslot * TC_BM + row] = col;
+                }
+                float mv = cval[row]; int ms = 0;
+#pragma unroll 8
+                for (int c = 1; c < TC_KC; c++) {
+                    const float x = cval[c * TC_BM + row];
+                    if (x < mv) { mv = x; ms = c; }
+                }
+                thresh = mv; minslot = ms;
+            };
+
+            for (int t = 0; t < n_tiles; t++, tile++) {
+                const int acc = tile & 1;
+                mbar_wait(ACC_FULL(acc), (tile >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float v[32];
+                    __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
+                    tmem_ld32(taddr + (uint32_t)c0, v);
+                    const int col0 = t * BN + c0;
+                    if (DUMP) {
+                        if (valid)
+                            for (int c = 0; c < 32; c++)
+                                if (col0 + c < p.n_items) p.dump[(int64_t)q * p.n_items + col0 + c] = v[c];
+                    }
+                    float m = v[0];
+#pragma unroll
+                    for (int c = 1; c < 32; c++) m = fmaxf(m, v[c]);
+                    const float bm = p.bmax_chunk ? __ldg(p.bmax_chunk + (col0 >> 5)) : 0.f;
+                    if (valid && (m + bm > thresh || count < TC_KC)) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const float s = p.bias ? v[c] + __ldg(p.bias + min(col0 + c, p.n_items - 1)) : v[c];
+                            if (s > thresh || count < TC_KC) try_insert(s, col0 + c);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
+            }
+
+            // ---- exact re-rank of this warp's 32 rows (one row at a time, one candidate per lane)
+            __syncwarp();
+            for (int r = 0; r < 32; r++) {
+                const int rrow = quad * 32 + r;
+                const int rq = mb * TC_BM + rrow;
+                if (rq >= p.n_sel) break;                                 // warp-uniform
+                const int ru = p.user_begin + rq;
+                const int rcount = __shfl_sync(0xffffffffu, count, r);
+                const float rthresh = __shfl_sync(0xffffffffu, thresh, r);
+                const int my_idx = lane < rcount ? cidx[lane * TC_BM + rrow] : 0x7fffffff;
+                float my_val = NEG;
+                const float *ur = p.U + (int64_t)ru * p.ld;
+                for (int c = 0; c < rcount; c++) {
+                    const int it = __shfl_sync(0xffffffffu, my_idx, c);
+                    const float *vr = p.V + (int64_t)it * p.ld;
+                    float a = 0.f;
+                    for (int kk = lane; kk < p.d; kk += 32) a += ur[kk] * vr[kk];      // same order as score_topk.cu
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                    const float e = (p.bias ? p.bias[it] : 0.f) + a;
+                    if (lane == c) my_val = e;
+                }
+                // bitonic sort over 32 lanes: (score desc, index asc)
+                float sv = my_val; int si = my_idx;
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, sv, j);
+                        const int oi = __shfl_xor_sync(0xffffffffu, si, j);
+                        const bool up = ((lane & kk) == 0);              // ascending rank order in this block
+                        const bool lower = ((lane & j) == 0);
+                        const bool other_first = cand_better(ov, oi, sv, si);
+                        const bool take = (up == lower) ? other_first : !other_first;
+                        if (take) { sv = ov; si = oi; }
+                    }
+                }
+                // certification: k-th exact score must clear tau + eps_u (only if something was rejected)
+                const float un = p.unorm[rq];
+                const float eps = p.eps_scale * un * p.vstat[0] + 1e-6f * (un * p.vstat[0] + p.vstat[1]);
+                const float kth = __shfl_sync(0xffffffffu, sv, p.k - 1);
+                const bool full = rcount >= TC_KC;
+                const bool certified = !full || (kth > rthresh + eps);
+                if (lane < p.k) {
+                    const bool ok = lane < rcount && sv > NEG;
+                    p.out_idx[(int64_t)rq * p.k + lane] = ok ? si : -1;
+                    p.out_val[(int64_t)rq * p.k + lane] = ok ? sv : NEG;
+                }
+                if (!certified && lane == 0) {
+                    const int slot = atomicAdd(p.flag_count, 1);
+                    p.flag_list[slot] = rq;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---------------------------------------------------------------- preparation kernels
+// fp32 rows [n, ld] (first d valid) -> bf16 rows [n, KP] zero padded; row norms; optional max
+__global__ void tc_convert_kernel(const float *src, int64_t n, int d, int ld, int row0, __nv_bfloat16 *dst, int KP,
+                                  float *norms, float *norm_max) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float wmax = 0.f;
+    for (; w < n; w += nw) {
+        const float *r = src + (row0 + w) * (int64_t)ld;
+        float ss = 0.f;
+        for (int k = lane; k < KP; k += 32) {
+            const float x = k < d ? r[k] : 0.f;
+            ss += x * x;
+            dst[w * KP + k] = __float2bfloat16_rn(x);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float nr = sqrtf(ss) * (1.f + 1e-6f);
+        if (norms && lane == 0) norms[w] = nr;
+        wmax = fmaxf(wmax, nr);
+    }
+    if (norm_max && lane == 0 && wmax > 0.f) atomicMax(reinterpret_cast<int *>(norm_max), __float_as_int(wmax));
+}
+
+__global__ void tc_bias_kernel(const float *bias, int32_t n_items, float *bmax_chunk, float *babs_max) {
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nchunks = (n_items + 31) / 32;
+    if (chunk >= nchunks) return;
+    float m = -CUDART_INF_F, a = 0.f;
+    for (int c = chunk * 32; c < min(chunk * 32 + 32, n_items); c++) { m = fmaxf(m, bias[c]); a = fmaxf(a, fabsf(bias[c])); }
+    bmax_chunk[chunk] = m;
+    atomicMax(reinterpret_cast<int *>(babs_max), __float_as_int(a));
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, void *base, uint64_t rows, int KP, uint32_t box_rows) {
+    EncodeFn enc = get_encode();
+    if (!enc) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KP * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return EB_OK;
+}
+
+static inline size_t al(size_t x) { return (x + 1023) / 1024 * 1024; }
+
+struct TcLayout {
+    size_t ubf, vbf, unorm, vstat, bmax, flag_count, flag_list, exact_ws, total, exact_bytes;
+    int KP;
+};
+
+static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d) {
+    TcLayout L;
+    L.KP = (d + 63) / 64 * 64;
+    size_t off = 0;
+    L.ubf = off; off += al((size_t)n_sel * L.KP * 2);
+    L.vbf = off; off += al((size_t)n_items * L.KP * 2);
+    L.unorm = off; off += al((size_t)n_sel * 4);
+    L.vstat = off; off += al(64);
+    L.bmax = off; off += al(((size_t)n_items + 31) / 32 * 4);
+    L.flag_count = off; off += al(64);
+    L.flag_list = off; off += al((size_t)n_sel * 4);
+    L.exact_bytes = (size_t)eb_score_topk_workspace_bytes(n_sel < 4096 ? n_sel : 4096, n_items, 4);
+    L.exact_ws = off; off += al(L.exact_bytes);
+    L.total = off;
+    return L;
+}
+
+template <int KP, bool DUMP>
+static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
+    auto kern = score_topk_tc_kernel<KP, DUMP>;
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP>::SMEM));
+    int grid = sm_count();
+    if (grid > n_mblocks) grid = n_mblocks;
+    kern<<<grid, TC_THREADS, TcCfg<KP>::SMEM, st>>>(a, b, p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" size_t eb_score_topk_tc_workspace_bytes(int64_t n_sel, int32_t n_items, int d) {
+    if (n_sel < 1) n_sel = 1;
+    return tc_layout(n_sel, n_items, d).total;
+}
+
+// internal entry of score_topk.cu with an output-row map (re-check of uncertified users)
+extern "C" int eb_score_topk_f32_mapped(const float *U, const float *V, const float *item_bias, int32_t n_items, int d,
+                                        int ld, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                        const int32_t *positions, int32_t user_begin, int64_t n_sel, int k,
+                                        int32_t *out_idx, float *out_val, void *workspace, size_t workspace_bytes,
+                                        void *stream);
+
+extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
+                                    const int64_t *mask_indptr, const int32_t *mask_indices, int32_t user_begin,
+                                    int64_t n_sel, int k, int32_t *out_idx, float *out_val, float *dump,
+                                    void *workspace, size_t workspace_bytes, int64_t *stats_host, void *stream) {
+    EB_ARG(U && V && out_idx && out_val && workspace, "null pointer");
+    EB_ARG(d >= 1 && d <= 256 && ld >= d, "tensor-core scoring supports 1 <= d <= 256 (d=%d ld=%d)", d, ld);
+    EB_ARG(k >= 1 && k <= 16, "tensor-core scoring keeps 32 candidates per user: k must be <= 16 (k=%d); "
+                              "use eb_score_topk_f32 for longer lists", k);
+    EB_ARG(n_items >= 1 && n_sel >= 0 && n_sel < (1ll << 31), "bad sizes");
+    EB_ARG((mask_indptr == nullptr) == (mask_indices == nullptr), "mask CSR: both or neither");
+    if (n_sel == 0) return EB_OK;
+    int cc = 0;
+    if (int rc = eb_device_info(nullptr, &cc)) return rc;
+    if (cc < 100) return set_err(EB_ERR_CUDA, "tcgen05 path needs compute capability 10.x (got %d)", cc);
+    const TcLayout L = tc_layout(n_sel, n_items, d);
+    if (workspace_bytes < L.total) return set_err(EB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    __nv_bfloat16 *ubf = (__nv_bfloat16 *)(ws + L.ubf), *vbf = (__nv_bfloat16 *)(ws + L.vbf);
+    float *unorm = (float *)(ws + L.unorm), *vstat = (float *)(ws + L.vstat), *bmax = (float *)(ws + L.bmax);
+    int32_t *flag_count = (int32_t *)(ws + L.flag_count), *flag_list = (int32_t *)(ws + L.flag_list);
+    EB_CUDA(cudaMemsetAsync(vstat, 0, 64, st));
+    EB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
+    const int cgrid = sm_count() * 8;
+    tc_convert_kernel<<<cgrid, 256, 0, st>>>(U, n_sel, d, ld, user_begin, ubf, L.KP, unorm, nullptr);
+    tc_convert_kernel<<<cgrid, 256, 0, st>>>(V, n_items, d, ld, 0, vbf, L.KP, nullptr, vstat);
+    if (item_bias) tc_bias_kernel<<<((n_items + 31) / 32 + 255) / 256, 256, 0, st>>>(item_bias, n_items, bmax, vstat + 1);
+    EB_CUDA(cudaGetLastError());
+    CUtensorMap ma, mb;
+    const int BN = L.KP <= 128 ? 256 : 128;
+    if (int rc = make_map(&ma, ubf, (uint64_t)n_sel, L.KP, TC_BM)) return rc;
+    if (int rc = make_map(&mb, vbf, (uint64_t)n_items, L.KP, BN)) return rc;
+    TcParams p{};
+    p.U = U; p.V = V; p.bias = item_bias; p.d = d; p.ld = ld; p.n_items = n_items;
+    p.mask_indptr = mask_indptr; p.mask_indices = mask_indices; p.user_begin = user_begin; p.n_sel = (int32_t)n_sel; p.k = k;
+    p.unorm = unorm; p.vstat = vstat; p.bmax_chunk = item_bias ? bmax : nullptr;
+    p.out_idx = out_idx; p.out_val = out_val; p.flag_count = flag_count; p.flag_list = flag_list; p.dump = dump;
+    // bf16 RN: |x~-x| <= 2^-9|x|  =>  |u~.v~ - u.v| <= (2^-8 + 2^-18) ||u|| ||v||; +2% for fp32 accumulation and re-rank rounding
+    p.eps_scale = 1.02f * (1.f / 256.f);
+    const int n_mblocks = (int)((n_sel + TC_BM - 1) / TC_BM);
+    int rc;
+    const bool dmp = dump != nullptr;
+    switch (L.KP) {
+        case 64: rc = dmp ? launch_tc<64, true>(ma, mb, p, n_mblocks, st) : launch_tc<64, false>(ma, mb, p, n_mblocks, st); break;
+        case 128: rc = dmp ? launch_tc<128, true>(ma, mb, p, n_mblocks, st) : launch_tc<128, false>(ma, mb, p, n_mblocks, st); break;
+        case 192: rc = dmp ? launch_tc<192, true>(ma, mb, p, n_mblocks, st) : launch_tc<192, false>(ma, mb, p, n_mblocks, st); break;
+        default: rc = dmp ? launch_tc<256, true>(ma, mb, p, n_mblocks, st) : launch_tc<256, false>(ma, mb, p, n_mblocks, st); break;
+    }
+    if (rc) return rc;
+    int32_t flagged = 0;
+    EB_CUDA(cudaMemcpyAsync(&flagged, flag_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    if (stats_host) { stats_host[0] = flagged; stats_host[1] = L.KP; }
+    if (flagged > 0) {
+        // provably-exact re-check of the users the bound could not certify
+        rc = eb_score_topk_f32_mapped(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, flag_list, user_begin,
+                                      flagged, k, out_idx, out_val, ws + L.exact_ws, L.exact_bytes, stream);
+        if (rc) return rc;
+    }
+    return EB_OK;
+}

@@ -176,3 +176,31 @@ def score_topk(U, V, bias, d, k, mask_indptr=None, mask_indices=None, users=None
         check(fn(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr), _ptr(mask_indices),
                  _ptr(users), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(ws), ws.numel(), _stream(U)))
     return idx, val
+
+
+_ws_tc = _Workspace()
+
+
+def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_begin=0, n_sel=None, dump=False):
+    """Tensor-core scoring + top-k (fp32 tables); same result as score_topk().  Returns
+    (idx, val, stats) with stats = {"rechecked": users re-done by the exact kernel, "kp": padded K}
+    (+ "dump": dense approximate scores when dump=True, tests only)."""
+    _need_cuda(U, V, bias, mask_indptr, mask_indices)
+    assert U.dtype == torch.float32 and V.dtype == torch.float32 and U.stride(0) == V.stride(0)
+    if n_sel is None:
+        n_sel = U.shape[0] - user_begin
+    n_items = V.shape[0]
+    dev = U.device
+    idx = torch.empty((n_sel, k), dtype=torch.int32, device=dev)
+    val = torch.empty((n_sel, k), dtype=torch.float32, device=dev)
+    dmp = torch.zeros((n_sel, n_items), dtype=torch.float32, device=dev) if dump else None
+    ws = _ws_tc.get(lib().eb_score_topk_tc_workspace_bytes(n_sel, n_items, d), dev)
+    stats = (ctypes.c_int64 * 2)()
+    with torch.cuda.device(dev):
+        check(lib().eb_score_topk_tc_f32(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr),
+                                         _ptr(mask_indices), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(dmp),
+                                         _ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), _stream(U)))
+    out = {"rechecked": int(stats[0]), "kp": int(stats[1])}
+    if dump:
+        out["dump"] = dmp
+    return idx, val, out

@@ -143,6 +143,21 @@ int eb_score_topk_f64(const double *U, const double *V, const double *item_bias,
                       const int32_t *users, int32_t user_begin, int64_t n_sel, int k,
                       int32_t *out_idx, double *out_val, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Tensor-core path (tcgen05 + TMEM + TMA, bf16 mainloop, exact fp32 re-rank).  Same contract and
+ * same RESULT as eb_score_topk_f32 (identical index lists and scores): the kernel keeps the 32
+ * best bf16-approximate candidates per user, re-scores them exactly in fp32 and certifies the
+ * list with a rounding bound; users it cannot certify are re-done by the exact kernel inside
+ * this call.  Contiguous user range only, k <= 16, d <= 256, mask rows sorted ascending.
+ * dump (optional, tests): dense n_sel x n_items raw approximate scores.
+ * stats_host (optional, host int64[2]): [0] users re-done exactly, [1] padded K.
+ * Synchronises the stream once (to read the re-check count). */
+size_t eb_score_topk_tc_workspace_bytes(int64_t n_sel, int32_t n_items, int d);
+int eb_score_topk_tc_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
+                         const int64_t *mask_indptr, const int32_t *mask_indices,
+                         int32_t user_begin, int64_t n_sel, int k,
+                         int32_t *out_idx, float *out_val, float *dump,
+                         void *workspace, size_t workspace_bytes, int64_t *stats_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
