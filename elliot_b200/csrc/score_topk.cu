@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(const ScoreParams
         for (int it = warp; it < p.n_items; it += 8) {
             const T *vr = p.V + (int64_t)it * p.ld;
             T acc = 0;
-            for (int k = lane; k < p.d; k += 32) acc += su[k] * vr[k];
+            for (int k = lane; k < p.d; k += 32) acc = fma(su[k], vr[k], acc);   // score_topk_tc.cu re-rank mirrors this order
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             if (lane == 0) s[it] = (p.bias ? p.bias[it] : (T)0) + acc;

@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t gets row (quadrant*32 + t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float *v) {
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -111,10 +112,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, 128-byte swizzle (what TMA SWIZZLE_128B writes for
 // a {64 bf16, rows} box): rows are 128 B apart, 8-row groups 1024 B apart.
@@ -151,33 +152,113 @@ struct TcParams {
     int32_t *flag_list;          // their positions q in [0, n_sel)
     float *dump;                 // optional dense n_sel x n_items approximate scores (tests)
     float eps_scale;             // c in eps_u = c * ||u|| * max||v|| + 1e-6 * (...)
+    long long *prof;             // optional per-kernel cycle counters (8 values), profiling only
+    int debug_mode;              // profiling only: 1 = TMEM read + max only, 2 = no compaction (results invalid)
 };
+
+constexpr int TC_BUF = 64;        // append buffer per user row (top-KC kept + up to BUF-KC pending)
+constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 columns if fewer than 8 slots are free
 
 template <int KP> struct TcCfg {
     static constexpr int KB = KP / 64;                       // 64-wide K blocks (one swizzle atom each)
-    static constexpr int BN = KP <= 128 ? 256 : 128;         // items per tile (UMMA N)
+    static constexpr int BN = KP <= 128 ? 256 : (KP == 192 ? 128 : 64);   // items per tile (UMMA N)
     static constexpr int STAGES = KP == 64 ? 3 : 2;
     static constexpr int A_BYTES = TC_BM * KP * 2;
     static constexpr int B_BYTES = BN * KP * 2;
-    static constexpr int CAND_BYTES = TC_BM * TC_KC * 8;
-    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + CAND_BYTES + 256;
+    static constexpr int CAND_BYTES = TC_BM * TC_BUF * 8;
+    static constexpr int SMEM = A_BYTES + STAGES * B_BYTES + CAND_BYTES + 256;
 };
 
 __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
-template <int KP, bool DUMP>
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+constexpr uint32_t TC_KEY_NEG = 0x007FFFC0u;     // sortable key of -inf with the tie-break bits cleared
+
+__device__ __forceinline__ uint32_t tc_key_of(float f, int pos) {   // order-preserving float->uint, low 6 bits = tie-break
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t k = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    return (k & ~63u) | (uint32_t)(63 - pos);
+}
+__device__ __forceinline__ float tc_upper_of(uint32_t key) {       // largest float whose key could be `key`
+    const uint32_t k = key | 63u;
+    const uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(b);
+}
+
+// Warp-cooperative compaction of ONE row of the candidate buffer (all 32 lanes call it together):
+// rank the row's 64 keys by counting (broadcast reads, no shuffles), keep ranks < KC in sorted order,
+// refill the rest with -inf.  Returns (number of valid kept entries, bits of the new threshold).
+// Deliberately NOT inlined: it is called from every 8-column group of the unrolled scan and the
+// kernel must stay inside the instruction cache.
+__device__ __noinline__ uint2 tc_compact_row(uint32_t bk, uint32_t bi, int rrow, int lane, int rl, const int32_t *mrow,
+                                             int n_items) {
+    const int p0 = (lane + rrow) & 63, p1 = (lane + 32 + rrow) & 63;
+    uint32_t k0 = (uint32_t)lds_s32(bk + 4u * p0), k1 = (uint32_t)lds_s32(bk + 4u * p1);
+    int i0 = lds_s32(bi + 4u * p0), i1 = lds_s32(bi + 4u * p1);
+    // train items (-inf in the reference) and the zero rows TMA pads past the catalogue
+    bool d0 = false, d1 = false;
+    if (k0 > (TC_KEY_NEG | 63u)) d0 = i0 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i0));
+    if (k1 > (TC_KEY_NEG | 63u)) d1 = i1 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i1));
+    if (d0) { k0 = TC_KEY_NEG | (uint32_t)(63 - p0); sts_s32(bk + 4u * p0, (int)k0); }
+    if (d1) { k1 = TC_KEY_NEG | (uint32_t)(63 - p1); sts_s32(bk + 4u * p1, (int)k1); }
+    __syncwarp();
+    int r0 = 0, r1 = 0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+        uint32_t x0, x1, x2, x3;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(bk + 4u * j));
+        r0 += (x0 > k0) + (x1 > k0) + (x2 > k0) + (x3 > k0);
+        r1 += (x0 > k1) + (x1 > k1) + (x2 > k1) + (x3 > k1);
+    }
+    __syncwarp();                     // all reads done before the row is rewritten
+    const int n0 = (r0 + rrow) & 63, n1 = (r1 + rrow) & 63;
+    const bool keep0 = r0 < TC_KC && k0 > (TC_KEY_NEG | 63u), keep1 = r1 < TC_KC && k1 > (TC_KEY_NEG | 63u);
+    sts_s32(bk + 4u * n0, (int)(keep0 ? ((k0 & ~63u) | (uint32_t)(63 - n0)) : (TC_KEY_NEG | (uint32_t)(63 - n0))));
+    sts_s32(bk + 4u * n1, (int)(keep1 ? ((k1 & ~63u) | (uint32_t)(63 - n1)) : (TC_KEY_NEG | (uint32_t)(63 - n1))));
+    if (keep0) sts_s32(bi + 4u * n0, i0);
+    if (keep1) sts_s32(bi + 4u * n1, i1);
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, keep0)) + __popc(__ballot_sync(0xffffffffu, keep1));
+    __syncwarp();
+    const float th = nvalid == TC_KC ? tc_upper_of((uint32_t)lds_s32(bk + 4u * ((TC_KC - 1 + rrow) & 63))) : -CUDART_INF_F;
+    return make_uint2((uint32_t)nvalid, __float_as_uint(th));
+}
+
+// compaction of all rows of this warp selected by `todo`; returns the calling lane's new (cnt, thresh)
+__device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint32_t cidx, int quad, int lane, int mlen,
+                                              int64_t mbeg, const int32_t *mask_indices, int n_items, int cnt, float thresh) {
+    __syncwarp();
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int rrow = quad * 32 + r;
+        const int rl = __shfl_sync(0xffffffffu, mlen, r);
+        const int64_t rb = __shfl_sync(0xffffffffu, mbeg, r);
+        const uint2 res = tc_compact_row(ckey + 256u * (uint32_t)rrow, cidx + 256u * (uint32_t)rrow, rrow, lane, rl,
+                                         mask_indices + rb, n_items);
+        if (lane == r) {
+            cnt = (int)res.x;
+            if (res.x == TC_KC) thresh = __uint_as_float(res.y);
+        }
+    }
+    __syncwarp();
+    return make_uint2((uint32_t)cnt, __float_as_uint(thresh));
+}
+
+template <int KP, bool DUMP, bool HAS_BIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using C = TcCfg<KP>;
     constexpr int KB = C::KB, BN = C::BN, S = C::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
     uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
-    float *cval = reinterpret_cast<float *>(sB + S * C::B_BYTES);            // [KC][128]
-    int *cidx = reinterpret_cast<int *>(cval + TC_KC * TC_BM);               // [KC][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(cidx + TC_KC * TC_BM);
-    // barrier indices
+    const uint32_t cval = smem_u32(sB + S * C::B_BYTES);                     // float [BUF][128]
+    const uint32_t cidx = cval + TC_BUF * TC_BM * 4;                         // int   [BUF][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + S * C::B_BYTES + C::CAND_BYTES);
     const uint32_t bar0 = smem_u32(bars);
     auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(S + s); };
@@ -191,6 +272,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int n_mblocks = (p.n_sel + TC_BM - 1) / TC_BM;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(sm) & 1023u) __trap();             // SWIZZLE_128B tiles need 1024-byte alignment
         for (int s = 0; s < S; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
         for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
@@ -255,113 +337,172 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;             // row inside the 128-user block
         const float NEG = -CUDART_INF_F;
+        // candidate buffer: row-major [128 rows][64 slots] of sortable keys + item ids; logical slot s of row r
+        // lives at physical position (s + r) & 63 (rotation: conflict-free appends AND conflict-free row reads)
+        const uint32_t ckey = cval;                   // uint32 keys
         uint32_t tile = 0;
+        long long c_wait = 0, c_ld = 0, c_scan = 0, c_comp = 0, c_rank = 0, n_comp = 0, n_slow = 0, n_grp = 0;
+        const bool prof = p.prof != nullptr && warp == 2;
         for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x) {
             const int q = mb * TC_BM + row;           // position in the selected user range
             const bool valid = q < p.n_sel;
             const int u = p.user_begin + (valid ? q : 0);
-            const int32_t *mrow = nullptr; int mlen = 0;
-            if (valid && p.mask_indptr) {
-                const int64_t b0 = p.mask_indptr[u];
-                mrow = p.mask_indices + b0; mlen = (int)(p.mask_indptr[u + 1] - b0);
-            }
-            int count = 0, minslot = 0;
-            float thresh = NEG;                       // min of the kept set once it is full
-
-            auto try_insert = [&](float s, int col) {
-                if (col >= p.n_items) return;         // TMA zero-filled rows past the catalogue
-                if (mrow && contains_sorted(mrow, mlen, col)) return;   // train item -> -inf
-                if (count < TC_KC) {
-                    cval[count * TC_BM + row] = s; cidx[count * TC_BM + row] = col; count++;
-                    if (count < TC_KC) return;
-                } else {
-                    cval[minslot * TC_BM + row] = s; cidx[minslot * TC_BM + row] = col;
-                }
-                float mv = cval[row]; int ms = 0;
+            int64_t mbeg = 0; int mlen = 0;
+            if (valid && p.mask_indptr) { mbeg = p.mask_indptr[u]; mlen = (int)(p.mask_indptr[u + 1] - mbeg); }
+            int cnt = 0;                              // filled logical slots of my row
+            float thresh = (valid && p.debug_mode != 1) ? NEG : CUDART_INF_F;   // upper bound of everything dropped so far
+            const uint32_t my_key = ckey + 256u * (uint32_t)row, my_idx = cidx + 256u * (uint32_t)row;
+            // invariant: logical slots >= cnt hold -inf keys
 #pragma unroll 8
-                for (int c = 1; c < TC_KC; c++) {
-                    const float x = cval[c * TC_BM + row];
-                    if (x < mv) { mv = x; ms = c; }
-                }
-                thresh = mv; minslot = ms;
+            for (int sl = 0; sl < TC_BUF; sl++) sts_s32(my_key + 4u * (uint32_t)sl, (int)(TC_KEY_NEG | (uint32_t)(63 - sl)));
+            __syncwarp();
+
+            auto compact = [&](uint32_t todo) {
+                const uint2 res = tc_compact_rows(todo, ckey, cidx, quad, lane, mlen, mbeg, p.mask_indices, p.n_items, cnt, thresh);
+                cnt = (int)res.x; thresh = __uint_as_float(res.y);
             };
 
             for (int t = 0; t < n_tiles; t++, tile++) {
                 const int acc = tile & 1;
+                long long t0 = prof ? clock64() : 0;
                 mbar_wait(ACC_FULL(acc), (tile >> 1) & 1);
                 tc_fence_after();
+                if (prof) c_wait += clock64() - t0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    float v[32];
-                    __syncwarp();                     // tcgen05.ld is .sync.aligned: reconverge after the divergent insert path
-                    tmem_ld32(taddr + (uint32_t)c0, v);
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    float v[64];
+                    __syncwarp();                     // tcgen05.ld is .sync.aligned
+                    long long t1 = prof ? clock64() : 0;
+                    tmem_ld32_nowait(taddr + (uint32_t)c0, v);
+                    tmem_ld32_nowait(taddr + (uint32_t)c0 + 32u, v + 32);
+                    tmem_ld_wait();
+                    if (prof) c_ld += clock64() - t1;
+                    long long t2 = prof ? clock64() : 0;
                     const int col0 = t * BN + c0;
                     if (DUMP) {
                         if (valid)
-                            for (int c = 0; c < 32; c++)
+                            for (int c = 0; c < 64; c++)
                                 if (col0 + c < p.n_items) p.dump[(int64_t)q * p.n_items + col0 + c] = v[c];
                     }
-                    float m = v[0];
+                    // max of each group of 8 columns (fast reject), 3-input max trees
+                    float g[8];
 #pragma unroll
-                    for (int c = 1; c < 32; c++) m = fmaxf(m, v[c]);
-                    const float bm = p.bmax_chunk ? __ldg(p.bmax_chunk + (col0 >> 5)) : 0.f;
-                    if (valid && (m + bm > thresh || count < TC_KC)) {
-#pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const float s = p.bias ? v[c] + __ldg(p.bias + min(col0 + c, p.n_items - 1)) : v[c];
-                            if (s > thresh || count < TC_KC) try_insert(s, col0 + c);
-                        }
+                    for (int s8 = 0; s8 < 8; s8++) {
+                        const float *w = v + s8 * 8;
+                        g[s8] = fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(fmaxf(w[3], w[4]), w[5]), fmaxf(w[6], w[7])));
                     }
+                    float bm0 = 0.f, bm1 = 0.f;
+                    if (HAS_BIAS) { bm0 = __ldg(p.bmax_chunk + (col0 >> 5)); bm1 = __ldg(p.bmax_chunk + min((col0 >> 5) + 1, (p.n_items - 1) >> 5)); }
+                    const float m64 = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) + bm0, fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])) + bm1);
+                    if (!__any_sync(0xffffffffu, m64 > thresh)) { if (prof) c_scan += clock64() - t2; continue; }
+                    n_slow++;
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) {
+                        const float bm = s8 < 4 ? bm0 : bm1;
+                        if (!__any_sync(0xffffffffu, g[s8] + bm > thresh)) continue;
+                        n_grp++;
+                        const uint32_t todo = __ballot_sync(0xffffffffu, cnt > TC_BUF - TC_SLACK);
+                        if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > TC_BUF - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
+                        // branch-free append of the group's survivors: predicates first, exclusive prefix of the
+                        // predicates gives each survivor its slot (no serial dependency through cnt)
+                        float sc[8]; uint32_t tk[8]; int ofs[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int cc = s8 * 8 + c;
+                            sc[c] = HAS_BIAS ? v[cc] + __ldg(p.bias + min(col0 + cc, p.n_items - 1)) : v[cc];
+                            tk[c] = sc[c] > thresh ? 1u : 0u;
+                        }
+                        ofs[0] = 0;
+#pragma unroll
+                        for (int c = 1; c < 8; c++) ofs[c] = ofs[c - 1] + (int)tk[c - 1];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int pos = (cnt + ofs[c] + row) & 63;
+                            const uint32_t key = tc_key_of(sc[c], pos);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %0, 0;\n\t"
+                                "@p st.shared.u32 [%1], %2;\n\t"
+                                "@p st.shared.s32 [%3], %4;\n\t}"
+                                ::"r"(tk[c]), "r"(my_key + 4u * (uint32_t)pos), "r"(key), "r"(my_idx + 4u * (uint32_t)pos),
+                                  "r"(col0 + s8 * 8 + c)
+                                : "memory");
+                        }
+                        cnt += ofs[7] + (int)tk[7];
+                    }
+                    if (prof) c_scan += clock64() - t2;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
             }
-
-            // ---- exact re-rank of this warp's 32 rows (one row at a time, one candidate per lane)
+            // final compaction: every row ends with its <= KC best unmasked candidates in logical slots 0..cnt-1
             __syncwarp();
+            long long t4 = prof ? clock64() : 0;
+            compact(__ballot_sync(0xffffffffu, valid));
+
+            const float vmax_n = p.vstat[0], bmax_a = p.vstat[1];
+            const float my_unorm = valid ? p.unorm[q] : 0.f;
+            // ---- exact re-rank of this warp's 32 rows: lane l re-scores candidate l of the row in fp32 with the
+            // SAME operation order as score_topk.cu (32 strided partial sums, then the xor-butterfly tree)
             for (int r = 0; r < 32; r++) {
                 const int rrow = quad * 32 + r;
                 const int rq = mb * TC_BM + rrow;
                 if (rq >= p.n_sel) break;                                 // warp-uniform
                 const int ru = p.user_begin + rq;
-                const int rcount = __shfl_sync(0xffffffffu, count, r);
+                const int rcount = __shfl_sync(0xffffffffu, cnt, r);
                 const float rthresh = __shfl_sync(0xffffffffu, thresh, r);
-                const int my_idx = lane < rcount ? cidx[lane * TC_BM + rrow] : 0x7fffffff;
-                float my_val = NEG;
-                const float *ur = p.U + (int64_t)ru * p.ld;
-                for (int c = 0; c < rcount; c++) {
-                    const int it = __shfl_sync(0xffffffffu, my_idx, c);
-                    const float *vr = p.V + (int64_t)it * p.ld;
-                    float a = 0.f;
-                    for (int kk = lane; kk < p.d; kk += 32) a += ur[kk] * vr[kk];      // same order as score_topk.cu
+                const bool have = lane < rcount;
+                const int my_i = have ? lds_s32(cidx + 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63)) : 0x7fffffff;
+                float my_v = NEG;
+                if (have) {
+                    const float *ur = p.U + (int64_t)ru * p.ld;
+                    const float *vr = p.V + (int64_t)my_i * p.ld;
+                    float ps[32];
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-                    const float e = (p.bias ? p.bias[it] : 0.f) + a;
-                    if (lane == c) my_val = e;
+                    for (int tt = 0; tt < 32; tt++) ps[tt] = 0.f;
+                    for (int base = 0; base < p.d; base += 32) {
+#pragma unroll
+                        for (int tt = 0; tt < 32; tt += 4) {
+                            if (base + tt + 3 < p.d) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(ur + base + tt));
+                                const float4 b4 = *reinterpret_cast<const float4 *>(vr + base + tt);
+                                ps[tt] = fmaf(a4.x, b4.x, ps[tt]); ps[tt + 1] = fmaf(a4.y, b4.y, ps[tt + 1]);
+                                ps[tt + 2] = fmaf(a4.z, b4.z, ps[tt + 2]); ps[tt + 3] = fmaf(a4.w, b4.w, ps[tt + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; e++)
+                                    if (base + tt + e < p.d) ps[tt + e] = fmaf(__ldg(ur + base + tt + e), vr[base + tt + e], ps[tt + e]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                        for (int tt = 0; tt < off; tt++) ps[tt] = ps[tt] + ps[tt + off];
+                    my_v = (HAS_BIAS ? p.bias[my_i] : 0.f) + ps[0];
                 }
                 // bitonic sort over 32 lanes: (score desc, index asc)
-                float sv = my_val; int si = my_idx;
+                float sv = my_v; int si = my_i;
 #pragma unroll
                 for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
                     for (int j = kk >> 1; j > 0; j >>= 1) {
                         const float ov = __shfl_xor_sync(0xffffffffu, sv, j);
                         const int oi = __shfl_xor_sync(0xffffffffu, si, j);
-                        const bool up = ((lane & kk) == 0);              // ascending rank order in this block
+                        const bool up = ((lane & kk) == 0);
                         const bool lower = ((lane & j) == 0);
                         const bool other_first = cand_better(ov, oi, sv, si);
                         const bool take = (up == lower) ? other_first : !other_first;
                         if (take) { sv = ov; si = oi; }
                     }
                 }
-                // certification: k-th exact score must clear tau + eps_u (only if something was rejected)
-                const float un = p.unorm[rq];
-                const float eps = p.eps_scale * un * p.vstat[0] + 1e-6f * (un * p.vstat[0] + p.vstat[1]);
+                // certification: the k-th exact score must clear tau + eps_u (tau = -inf if nothing was ever dropped)
+                const float un = __shfl_sync(0xffffffffu, my_unorm, r);
+                const float eps = p.eps_scale * un * vmax_n + 1e-6f * (un * vmax_n + bmax_a);
                 const float kth = __shfl_sync(0xffffffffu, sv, p.k - 1);
-                const bool full = rcount >= TC_KC;
-                const bool certified = !full || (kth > rthresh + eps);
+                const bool certified = !(rthresh > NEG) || (kth > rthresh + eps) || p.debug_mode != 0;
                 if (lane < p.k) {
                     const bool ok = lane < rcount && sv > NEG;
                     p.out_idx[(int64_t)rq * p.k + lane] = ok ? si : -1;
@@ -373,6 +514,11 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
             }
             __syncwarp();
+            if (prof) c_rank += clock64() - t4;
+        }
+        if (prof && lane == 0 && blockIdx.x == 0) {
+            p.prof[0] = c_wait; p.prof[1] = c_ld; p.prof[2] = c_scan; p.prof[3] = c_comp; p.prof[4] = c_rank;
+            p.prof[5] = n_comp; p.prof[6] = n_slow; p.prof[7] = n_grp;
         }
     }
     tc_fence_before();
@@ -462,7 +608,7 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d) {
     L.unorm = off; off += al((size_t)n_sel * 4);
     L.vstat = off; off += al(64);
     L.bmax = off; off += al(((size_t)n_items + 31) / 32 * 4);
-    L.flag_count = off; off += al(64);
+    L.flag_count = off; off += al(256);
     L.flag_list = off; off += al((size_t)n_sel * 4);
     L.exact_bytes = (size_t)eb_score_topk_workspace_bytes(n_sel < 4096 ? n_sel : 4096, n_items, 4);
     L.exact_ws = off; off += al(L.exact_bytes);
@@ -470,15 +616,22 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d) {
     return L;
 }
 
-template <int KP, bool DUMP>
-static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    auto kern = score_topk_tc_kernel<KP, DUMP>;
+template <int KP, bool DUMP, bool HAS_BIAS>
+static int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
+    auto kern = score_topk_tc_kernel<KP, DUMP, HAS_BIAS>;
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP>::SMEM));
     int grid = sm_count();
     if (grid > n_mblocks) grid = n_mblocks;
     kern<<<grid, TC_THREADS, TcCfg<KP>::SMEM, st>>>(a, b, p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
+}
+
+template <int KP>
+static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
+    const bool hb = p.bias != nullptr;
+    if (p.dump) return hb ? launch_tc3<KP, true, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, true, false>(a, b, p, n_mblocks, st);
+    return hb ? launch_tc3<KP, false, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, false, false>(a, b, p, n_mblocks, st);
 }
 
 }  // namespace eb
@@ -519,14 +672,14 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     float *unorm = (float *)(ws + L.unorm), *vstat = (float *)(ws + L.vstat), *bmax = (float *)(ws + L.bmax);
     int32_t *flag_count = (int32_t *)(ws + L.flag_count), *flag_list = (int32_t *)(ws + L.flag_list);
     EB_CUDA(cudaMemsetAsync(vstat, 0, 64, st));
-    EB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
+    EB_CUDA(cudaMemsetAsync(flag_count, 0, 256, st));
     const int cgrid = sm_count() * 8;
     tc_convert_kernel<<<cgrid, 256, 0, st>>>(U, n_sel, d, ld, user_begin, ubf, L.KP, unorm, nullptr);
     tc_convert_kernel<<<cgrid, 256, 0, st>>>(V, n_items, d, ld, 0, vbf, L.KP, nullptr, vstat);
     if (item_bias) tc_bias_kernel<<<((n_items + 31) / 32 + 255) / 256, 256, 0, st>>>(item_bias, n_items, bmax, vstat + 1);
     EB_CUDA(cudaGetLastError());
     CUtensorMap ma, mb;
-    const int BN = L.KP <= 128 ? 256 : 128;
+    const int BN = L.KP <= 128 ? 256 : (L.KP == 192 ? 128 : 64);
     if (int rc = make_map(&ma, ubf, (uint64_t)n_sel, L.KP, TC_BM)) return rc;
     if (int rc = make_map(&mb, vbf, (uint64_t)n_items, L.KP, BN)) return rc;
     TcParams p{};
@@ -536,20 +689,24 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     p.out_idx = out_idx; p.out_val = out_val; p.flag_count = flag_count; p.flag_list = flag_list; p.dump = dump;
     // bf16 RN: |x~-x| <= 2^-9|x|  =>  |u~.v~ - u.v| <= (2^-8 + 2^-18) ||u|| ||v||; +2% for fp32 accumulation and re-rank rounding
     p.eps_scale = 1.02f * (1.f / 256.f);
+    { const char *dbg = getenv("EB_TC_DEBUG"); p.debug_mode = dbg ? atoi(dbg) : 0; }
+    p.prof = (stats_host && getenv("EB_TC_PROF")) ? (long long *)(flag_count + 16) : nullptr;
     const int n_mblocks = (int)((n_sel + TC_BM - 1) / TC_BM);
     int rc;
-    const bool dmp = dump != nullptr;
     switch (L.KP) {
-        case 64: rc = dmp ? launch_tc<64, true>(ma, mb, p, n_mblocks, st) : launch_tc<64, false>(ma, mb, p, n_mblocks, st); break;
-        case 128: rc = dmp ? launch_tc<128, true>(ma, mb, p, n_mblocks, st) : launch_tc<128, false>(ma, mb, p, n_mblocks, st); break;
-        case 192: rc = dmp ? launch_tc<192, true>(ma, mb, p, n_mblocks, st) : launch_tc<192, false>(ma, mb, p, n_mblocks, st); break;
-        default: rc = dmp ? launch_tc<256, true>(ma, mb, p, n_mblocks, st) : launch_tc<256, false>(ma, mb, p, n_mblocks, st); break;
+        case 64: rc = launch_tc<64>(ma, mb, p, n_mblocks, st); break;
+        case 128: rc = launch_tc<128>(ma, mb, p, n_mblocks, st); break;
+        case 192: rc = launch_tc<192>(ma, mb, p, n_mblocks, st); break;
+        default: rc = launch_tc<256>(ma, mb, p, n_mblocks, st); break;
     }
     if (rc) return rc;
     int32_t flagged = 0;
     EB_CUDA(cudaMemcpyAsync(&flagged, flag_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EB_CUDA(cudaStreamSynchronize(st));
-    if (stats_host) { stats_host[0] = flagged; stats_host[1] = L.KP; }
+    if (stats_host) {
+        stats_host[0] = flagged; stats_host[1] = L.KP;
+        if (p.prof) EB_CUDA(cudaMemcpy(stats_host + 2, p.prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
     if (flagged > 0) {
         // provably-exact re-check of the users the bound could not certify
         rc = eb_score_topk_f32_mapped(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, flag_list, user_begin,

@@ -195,12 +195,12 @@ def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_be
     val = torch.empty((n_sel, k), dtype=torch.float32, device=dev)
     dmp = torch.zeros((n_sel, n_items), dtype=torch.float32, device=dev) if dump else None
     ws = _ws_tc.get(lib().eb_score_topk_tc_workspace_bytes(n_sel, n_items, d), dev)
-    stats = (ctypes.c_int64 * 2)()
+    stats = (ctypes.c_int64 * 16)()
     with torch.cuda.device(dev):
         check(lib().eb_score_topk_tc_f32(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr),
                                          _ptr(mask_indices), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(dmp),
                                          _ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), _stream(U)))
-    out = {"rechecked": int(stats[0]), "kp": int(stats[1])}
+    out = {"rechecked": int(stats[0]), "kp": int(stats[1]), "prof": [int(x) for x in stats[2:10]]}
     if dump:
         out["dump"] = dmp
     return idx, val, out

@@ -149,7 +149,8 @@ int eb_score_topk_f64(const double *U, const double *V, const double *item_bias,
  * list with a rounding bound; users it cannot certify are re-done by the exact kernel inside
  * this call.  Contiguous user range only, k <= 16, d <= 256, mask rows sorted ascending.
  * dump (optional, tests): dense n_sel x n_items raw approximate scores.
- * stats_host (optional, host int64[2]): [0] users re-done exactly, [1] padded K.
+ * stats_host (optional, host int64[16]): [0] users re-done exactly, [1] padded K, [2..9] cycle
+ * counters of CTA 0 when the environment variable EB_TC_PROF is set (profiling aid).
  * Synchronises the stream once (to read the re-check count). */
 size_t eb_score_topk_tc_workspace_bytes(int64_t n_sel, int32_t n_items, int d);
 int eb_score_topk_tc_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
