@@ -39,6 +39,9 @@ SIGNATURES = {
                                   c_int, c_void, c_void, c_void, c_size, c_void]),
     "eb_score_topk_f64": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_void, c_i32, c_i64,
                                   c_int, c_void, c_void, c_void, c_size, c_void]),
+    "eb_bpr_batch_grad_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void,
+                                      c_i64, c_f32, c_f32, c_void, c_void]),
+    "eb_adam_dense_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),
     "eb_score_topk_tc_f32": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_i32, c_i64, c_int,
                                      c_void, c_void, c_void, c_void, c_size, c_void, c_void]),

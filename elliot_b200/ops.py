@@ -204,3 +204,23 @@ def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_be
     if dump:
         out["dump"] = dmp
     return idx, val, out
+
+
+def bpr_batch_grad_f32(Gu, Gi, Bi, dGu, dGi, dBi, d, tu, ti, tj, l_w, l_b, loss=None):
+    """Batch gradient of the BPRMF_batch loss (BPRMF_batch_model.py:57-75) into dense gradient tables."""
+    _need_cuda(Gu, Gi, Bi, dGu, dGi, dBi, tu, ti, tj, loss)
+    _chk_idx(tu, ti, tj)
+    assert Gu.stride(0) == Gi.stride(0) == dGu.stride(0) == dGi.stride(0)
+    with torch.cuda.device(Gu.device):
+        check(lib().eb_bpr_batch_grad_f32(_ptr(Gu), _ptr(Gi), _ptr(Bi), _ptr(dGu), _ptr(dGi), _ptr(dBi), d, Gu.stride(0),
+                                          _ptr(tu), _ptr(ti), _ptr(tj), tu.numel(), l_w, l_b, _ptr(loss), _stream(Gu)))
+
+
+def adam_dense_f32(var, m, v, grad, lr, step, beta1=0.9, beta2=0.999, eps=1e-7):
+    """Keras Adam over every element (TF 2.3 semantics for sparse gradients too); clears `grad`."""
+    _need_cuda(var, m, v, grad)
+    n = var.numel()
+    assert var.is_contiguous() and m.numel() == n and v.numel() == n and grad.numel() == n and n % 4 == 0
+    with torch.cuda.device(var.device):
+        check(lib().eb_adam_dense_f32(_ptr(var), _ptr(m), _ptr(v), _ptr(grad), n, lr, beta1, beta2, eps, step,
+                                      _stream(var)))

@@ -1,3 +1,4 @@
 """Model registry: the class names the reference resolves from the YAML model key
 (elliot/run.py:75, elliot/recommender/__init__.py)."""
 from .bprmf import BPRMF, MFModel  # noqa: F401
+from .bprmf_batch import BPRMF_batch, BPRMFBatchModel  # noqa: F401

@@ -143,6 +143,21 @@ int eb_score_topk_f64(const double *U, const double *V, const double *item_bias,
                       const int32_t *users, int32_t user_begin, int64_t n_sel, int k,
                       int32_t *out_idx, double *out_val, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Mini-batch BPR-MF with Adam (the reference's TensorFlow variant).
+ * Replaces BPRMF_batch_model.call/train_step (BPRMF_batch_model.py:46-80):
+ * eb_bpr_batch_grad_f32 accumulates the batch gradient of
+ *   sum softplus(-clip(x_pos-x_neg,-80,1e8)) + l_w(|gu|^2+|gpos|^2+|gneg|^2)/2 + l_b bpos^2/2 + l_b bneg^2/20
+ * into dense gradient tables (duplicates summed, like IndexedSlices);
+ * eb_adam_dense_f32 is Keras Adam applied to every element (TF 2.3 moves all rows even for
+ * sparse gradients) and clears the gradient.  lr_t = lr sqrt(1-b2^step)/(1-b1^step).
+ * ------------------------------------------------------------------------ */
+int eb_bpr_batch_grad_f32(const float *Gu, const float *Gi, const float *Bi, float *dGu, float *dGi, float *dBi,
+                          int d, int ld, const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                          float l_w, float l_b, double *loss, void *stream);
+int eb_adam_dense_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
+                      float eps, int64_t step, void *stream);
+
 /* Tensor-core path (tcgen05 + TMEM + TMA, bf16 mainloop, exact fp32 re-rank).  Same contract and
  * same RESULT as eb_score_topk_f32 (identical index lists and scores): the kernel keeps the 32
  * best bf16-approximate candidates per user, re-scores them exactly in fp32 and certifies the

@@ -1,0 +1,68 @@
+"""fp64 NumPy restatements of the reference's TensorFlow models.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: tensorflow==2.3.2 (requirements.txt:3) is absent from the build container and
+its source is not under /root/reference, so these follow the reference's model code line by
+line plus the published TF 2.3 semantics they rely on (stated per function).  Nothing here was
+checked against a TensorFlow run.
+"""
+import numpy as np
+
+
+def softplus(x):
+    return np.where(x > 0, x + np.log1p(np.exp(-np.abs(x))), np.log1p(np.exp(-np.abs(x))))
+
+
+def bprmf_batch_loss_and_grads(Gu, Gi, Bi, u, i, j, l_w, l_b):
+    """BPRMF_batch_model.call/train_step, BPRMF_batch_model.py:46-75.
+    TF semantics assumed: tf.nn.l2_loss(t) = sum(t**2)/2 over the gathered batch rows;
+    clip_by_value passes gradient only strictly inside (-80, 1e8); gradients w.r.t. the
+    variables are IndexedSlices whose duplicate indices are summed when applied."""
+    gu, gp, gn = Gu[u], Gi[i], Gi[j]
+    bp, bn = Bi[i], Bi[j]
+    raw = (bp + (gu * gp).sum(1)) - (bn + (gu * gn).sum(1))
+    diff = np.clip(raw, -80.0, 1e8)
+    loss = softplus(-diff).sum() + l_w * ((gu ** 2).sum() + (gp ** 2).sum() + (gn ** 2).sum()) / 2 \
+        + l_b * (bp ** 2).sum() / 2 + l_b * (bn ** 2).sum() / 2 / 10
+    g = np.where((raw > -80.0) & (raw < 1e8), -1.0 / (1.0 + np.exp(diff)), 0.0)
+    dGu = np.zeros_like(Gu); dGi = np.zeros_like(Gi); dBi = np.zeros_like(Bi)
+    np.add.at(dGu, u, g[:, None] * (gp - gn) + l_w * gu)
+    np.add.at(dGi, i, g[:, None] * gu + l_w * gp)
+    np.add.at(dGi, j, -g[:, None] * gu + l_w * gn)
+    np.add.at(dBi, i, g + l_b * bp)
+    np.add.at(dBi, j, -g + l_b * bn / 10)
+    return loss, dGu, dGi, dBi
+
+
+class KerasAdam:
+    """tf.optimizers.Adam(lr) as used at BPRMF_batch_model.py:44,77-78.  TF 2.3 OptimizerV2 Adam:
+    beta_1=0.9, beta_2=0.999, epsilon=1e-7, lr_t = lr*sqrt(1-b2^t)/(1-b1^t); the sparse apply
+    decays m and v and updates the variable for EVERY row (dense-equivalent with the summed
+    IndexedSlices gradient)."""
+
+    def __init__(self, lr, b1=0.9, b2=0.999, eps=1e-7):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, b1, b2, eps, 0
+        self.state = {}
+
+    def begin_step(self):
+        self.t += 1
+
+    def apply(self, name, var, grad):
+        m, v = self.state.setdefault(name, (np.zeros_like(var), np.zeros_like(var)))
+        lr_t = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        m *= self.b1; m += (1 - self.b1) * grad
+        v *= self.b2; v += (1 - self.b2) * grad * grad
+        var -= lr_t * m / (np.sqrt(v) + self.eps)
+
+
+def bprmf_batch_step(Gu, Gi, Bi, opt, u, i, j, l_w, l_b):
+    loss, dGu, dGi, dBi = bprmf_batch_loss_and_grads(Gu, Gi, Bi, u, i, j, l_w, l_b)
+    opt.begin_step()
+    opt.apply("Bi", Bi, dBi); opt.apply("Gu", Gu, dGu); opt.apply("Gi", Gi, dGi)
+    return loss
+
+
+def glorot_uniform(rng, shape):
+    """tf.initializers.GlorotUniform limits (values come from TF's own Philox stream, which
+    cannot be replayed here)."""
+    lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+    return rng.uniform(-lim, lim, size=shape)
