@@ -42,6 +42,11 @@ SIGNATURES = {
     "eb_bpr_batch_grad_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void,
                                       c_i64, c_f32, c_f32, c_void, c_void]),
     "eb_adam_dense_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_void]),
+    "eb_convert_bf16": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_i64, c_int, c_void]),
+    "eb_gemm_bf16_tn": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
+                                c_void]),
+    "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
+    "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),
     "eb_score_topk_tc_f32": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_i32, c_i64, c_int,
                                      c_void, c_void, c_void, c_void, c_size, c_void, c_void]),

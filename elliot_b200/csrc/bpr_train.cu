@@ -459,7 +459,7 @@ extern "C" int eb_bpr_step_host_f32(float *U, float *V, float *item_bias, int d,
         return rc;
     if (loss_dev && loss_host)
         EB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
-    EB_CUDA(cudaStreamSynchronize(st));
+    if (!(flags & 2)) EB_CUDA(cudaStreamSynchronize(st));
     return EB_OK;
 }
 

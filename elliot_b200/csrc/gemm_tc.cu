@@ -1,0 +1,285 @@
+// gemm_tc.cu — general bf16 tensor-core GEMM for the dense layers of MultiVAE / NeuMF.
+//
+//   C[M][N] (fp32, row stride ldc) = A[M][K] * B[N][K]^T  (+ bias[N]) (optional tanh / relu)
+//
+// Both operands are bf16, K-major (row-major with K contiguous), which is what the Keras Dense
+// layers of the reference need once weights are kept as [out][in]
+// (multi_vae_model.py:44-53,72-78; neural_matrix_factorization_model.py:57-70).  Backward GEMMs
+// use the same kernel on transposed copies (tc_convert_transpose_kernel).
+// Structure = score_topk_tc.cu without the top-k: persistent CTAs, warp 0 TMA producer
+// (4-stage ring of {A 128x64, B 128x64} bf16 tiles, 128B swizzle), warp 1 tcgen05.mma issuer
+// (M=128, N=128, K=16 per instruction, fp32 accumulators double-buffered in TMEM), warps 2-5
+// epilogue (tcgen05.ld -> bias/activation -> global).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace eb {
+
+constexpr int G_BM = 128, G_BN = 128, G_BK = 64, G_STAGES = 4, G_THREADS = 192;
+constexpr int G_STAGE_BYTES = (G_BM + G_BN) * G_BK * 2;      // 32 KB
+constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 256;
+
+// ---- PTX helpers (same encodings as score_topk_tc.cu)
+__device__ __forceinline__ uint32_t g_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void g_tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t g_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+__device__ __forceinline__ void g_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct GemmParams {
+    float *C;
+    int64_t ldc;
+    const float *bias;   // [N] or null
+    int M, N, K;
+    int act;             // 0 none, 1 tanh, 2 relu
+    float alpha;         // C = alpha * (A B^T) + bias, then activation
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + G_STAGES * G_STAGE_BYTES);
+    const uint32_t bar0 = g_smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(G_STAGES + s); };
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * G_STAGES + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * G_STAGES + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * G_STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + G_BM - 1) / G_BM, tiles_n = (p.N + G_BN - 1) / G_BN;
+    const int n_tiles = tiles_m * tiles_n;
+    const int k_blocks = (p.K + G_BK - 1) / G_BK;
+
+    if (threadIdx.x == 0) {
+        if (g_smem_u32(sm) & 1023u) __trap();
+        for (int s = 0; s < G_STAGES; s++) { g_mbar_init(FULL(s), 1); g_mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; a++) { g_mbar_init(ACC_FULL(a), 1); g_mbar_init(ACC_EMPTY(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(2 * G_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int tm = tile / tiles_n, tn = tile % tiles_n;
+                for (int kb = 0; kb < k_blocks; kb++) {
+                    g_mbar_wait(EMPTY(s), ph ^ 1);
+                    g_mbar_expect_tx(FULL(s), G_STAGE_BYTES);
+                    const uint32_t a_dst = g_smem_u32(sm + s * G_STAGE_BYTES), b_dst = a_dst + G_BM * G_BK * 2;
+                    g_tma_load_2d(a_dst, &tmA, FULL(s), kb * G_BK, tm * G_BM);
+                    g_tma_load_2d(b_dst, &tmB, FULL(s), kb * G_BK, tn * G_BN);
+                    if (++s == G_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: fp32 accum, bf16 A/B, K-major both, N=128, M=128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+            int s = 0; uint32_t ph = 0; uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                g_mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G_BN);
+                for (int kb = 0; kb < k_blocks; kb++) {
+                    g_mbar_wait(FULL(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = g_smem_u32(sm + s * G_STAGE_BYTES), b_addr = a_addr + G_BM * G_BK * 2;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        g_umma(d_tmem, g_desc_sw128(a_addr + k * 32), g_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    g_commit(EMPTY(s));
+                    if (++s == G_STAGES) { s = 0; ph ^= 1; }
+                }
+                g_commit(ACC_FULL(acc));
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int tm = tile / tiles_n, tn = tile % tiles_n;
+            const int acc = it & 1;
+            g_mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = tm * G_BM + quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * G_BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < G_BN; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)c0)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+                    float *crow = p.C + (int64_t)row * p.ldc;
+                    const int col0 = tn * G_BN + c0;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int col = col0 + c;
+                        if (col < p.N) {
+                            float x = p.alpha * __uint_as_float(r[c]) + (p.bias ? __ldg(p.bias + col) : 0.f);
+                            if (p.act == 1) x = tanhf(x);
+                            else if (p.act == 2) x = fmaxf(x, 0.f);
+                            crow[col] = x;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) g_mbar_arrive(ACC_EMPTY(acc));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * G_BN) : "memory");
+}
+
+// fp32 [R][C] (row stride ld) -> bf16 [R][dst_ld] (same layout, zero padded columns)
+__global__ void __launch_bounds__(256) tc_convert_kernel2(const float *__restrict__ src, int R, int C, int64_t ld,
+                                                          __nv_bfloat16 *__restrict__ dst, int64_t dst_ld) {
+    const int64_t total = (int64_t)R * dst_ld;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / dst_ld; const int c = (int)(e - r * dst_ld);
+        dst[e] = __float2bfloat16_rn(c < C ? src[r * ld + c] : 0.f);
+    }
+}
+// fp32 [R][C] -> bf16 [C][dst_ld] (transposed; columns r >= R zero padded); 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) tc_transpose_kernel(const float *__restrict__ src, int R, int C, int64_t ld,
+                                                           __nv_bfloat16 *__restrict__ dst, int64_t dst_ld) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        tile[j][tx] = (r < R && c < C) ? src[(int64_t)r * ld + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;
+        if (c < C && r < dst_ld) dst[(int64_t)c * dst_ld + r] = __float2bfloat16_rn(tile[tx][j]);
+    }
+}
+
+typedef CUresult (*GEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int g_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t K, uint64_t ld_elems, uint32_t box_rows) {
+    static GEncodeFn enc = nullptr;
+    if (!enc) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        enc = (GEncodeFn)fp;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+    cuuint32_t box[2] = {G_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return EB_OK;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld, void *dst_bf16, int64_t dst_ld, int transpose,
+                               void *stream) {
+    EB_ARG(src && dst_bf16 && rows >= 1 && cols >= 1 && ld >= cols, "bad argument");
+    EB_ARG(dst_ld % 8 == 0 && dst_ld >= (transpose ? rows : cols), "dst_ld must be a multiple of 8 and cover the row");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!transpose) {
+        int64_t grid = ((int64_t)rows * dst_ld + 255) / 256; const int64_t cap = (int64_t)sm_count() * 8; if (grid > cap) grid = cap;
+        tc_convert_kernel2<<<(unsigned)grid, 256, 0, st>>>(src, rows, cols, ld, (__nv_bfloat16 *)dst_bf16, dst_ld);
+    } else {
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((dst_ld + 31) / 32));
+        tc_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld, (__nv_bfloat16 *)dst_bf16, dst_ld);
+    }
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
+                               int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
+    EB_ARG(A_bf16 && B_bf16 && C, "null pointer");
+    EB_ARG(M >= 1 && N >= 1 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "bad shape M=%d N=%d K=%d", M, N, K);
+    EB_ARG(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA strides)");
+    EB_ARG(((uintptr_t)A_bf16 % 16) == 0 && ((uintptr_t)B_bf16 % 16) == 0, "operands must be 16-byte aligned");
+    EB_ARG(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh) or 2 (relu)");
+    CUtensorMap ma, mb;
+    if (int rc = g_make_map(&ma, A_bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM)) return rc;
+    if (int rc = g_make_map(&mb, B_bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, G_BN)) return rc;
+    GemmParams p{C, ldc, bias, M, N, K, act, alpha};
+    EB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    const int n_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+    int grid = sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    gemm_tc_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}

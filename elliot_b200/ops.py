@@ -82,7 +82,7 @@ def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0):
 
 
 def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, reg_pos, reg_neg, staging, loss_dev,
-                      loss_host, racy=False):
+                      loss_host, racy=False, sync=True):
     """End-to-end step from HOST (pinned) int32 triples; returns after the loss is back on the host."""
     _need_cuda(U, V, b, staging, loss_dev)
     n = tu_host.numel()
@@ -90,7 +90,7 @@ def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, r
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_host_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), _ptr(tu_host), _ptr(ti_host),
                                          _ptr(tj_host), n, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(staging),
-                                         _ptr(loss_dev), _ptr(loss_host), 1 if racy else 0, _stream(U)))
+                                         _ptr(loss_dev), _ptr(loss_host), (1 if racy else 0) | (0 if sync else 2), _stream(U)))
 
 
 class _Workspace:
@@ -224,3 +224,42 @@ def adam_dense_f32(var, m, v, grad, lr, step, beta1=0.9, beta2=0.999, eps=1e-7):
     with torch.cuda.device(var.device):
         check(lib().eb_adam_dense_f32(_ptr(var), _ptr(m), _ptr(v), _ptr(grad), n, lr, beta1, beta2, eps, step,
                                       _stream(var)))
+
+
+def table_delta_f32(cur, prev, delta):
+    _need_cuda(cur, prev, delta)
+    assert cur.is_contiguous() and prev.is_contiguous() and delta.is_contiguous() and cur.numel() % 4 == 0
+    with torch.cuda.device(cur.device):
+        check(lib().eb_table_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta), cur.numel(), _stream(cur)))
+
+
+def table_apply_delta_f32(cur, prev, delta_sum):
+    _need_cuda(cur, prev, delta_sum)
+    with torch.cuda.device(cur.device):
+        check(lib().eb_table_apply_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), cur.numel(), _stream(cur)))
+
+
+def to_bf16(src, transpose=False, out=None):
+    """fp32 [R][C] -> bf16 [R][pad8(C)] or (transpose) [C][pad8(R)], zero padded, via eb_convert_bf16."""
+    _need_cuda(src)
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    R, C = src.shape
+    rows, cols = (C, R) if transpose else (R, C)
+    ldd = (cols + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().eb_convert_bf16(_ptr(src), R, C, src.stride(0), _ptr(out), ldd, 1 if transpose else 0, _stream(src)))
+    return out
+
+
+def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
+    """C[M][N] fp32 = act(alpha * A[M][:K] @ B[N][:K]^T + bias) on the tensor cores (A, B bf16, K-major)."""
+    _need_cuda(A, B, bias, out)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().eb_gemm_bf16_tn(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), M, N, K, _ptr(bias),
+                                    alpha, act, _stream(A)))
+    return out

@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing for the hot path — one process per GPU, torch.distributed.
+
+Training: user rows are sharded (rank r owns a contiguous block of users and samples triples
+only for them, so user rows never move); the item table and item biases are REPLICATED and
+reconciled once per step by one all-reduce of the per-rank deltas (the path's only exchange
+step).  Scoring: users are sharded, V replicated, no collective.  The reference has no
+distributed code at all; exact mode is single-GPU by definition.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous block partition of n rows: sizes differ by at most one, concatenation covers [0, n)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def owner_of(row, n, world):
+    base, rem = divmod(n, world)
+    cut = rem * (base + 1)
+    return row // (base + 1) if row < cut else rem + (row - cut) // max(base, 1)
+
+
+class ReplicatedTableSync:
+    """Keeps replicated tables consistent across ranks:  T <- T_prev + sum_r (T_r - T_prev).
+
+    delta_fn / apply_fn default to the CUDA kernels (ops.table_delta_f32 / table_apply_delta_f32);
+    the CPU (gloo) tests inject torch equivalents to exercise the protocol without a GPU.
+    """
+
+    def __init__(self, tables, group=None, delta_fn=None, apply_fn=None):
+        from . import ops
+        self.tables = list(tables)
+        self.prev = [t.clone() for t in self.tables]
+        self.delta = [torch.empty_like(t) for t in self.tables]
+        self.group = group
+        self._delta = delta_fn or ops.table_delta_f32
+        self._apply = apply_fn or ops.table_apply_delta_f32
+
+    def sync(self):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        for t, p, d in zip(self.tables, self.prev, self.delta):
+            self._delta(t, p, d)
+            if world > 1:
+                dist.all_reduce(d, group=self.group)
+            self._apply(t, p, d)
+
+
+def gather_topk(idx_local, val_local, n_users, group=None):
+    """Concatenate user-sharded (idx, val) blocks in rank order (block partition => user order).
+    Shards may differ by one row: blocks are padded to the largest shard for the all_gather."""
+    world = dist.get_world_size(group)
+    sizes = [hi - lo for lo, hi in (shard_range(n_users, r, world) for r in range(world))]
+    mx, k = max(sizes), idx_local.shape[1]
+
+    def padded(t, fill):
+        if t.shape[0] == mx:
+            return t.contiguous()
+        out = torch.full((mx, k), fill, dtype=t.dtype, device=t.device)
+        out[:t.shape[0]] = t
+        return out
+    out_i = [torch.empty((mx, k), dtype=idx_local.dtype, device=idx_local.device) for _ in range(world)]
+    out_v = [torch.empty((mx, k), dtype=val_local.dtype, device=val_local.device) for _ in range(world)]
+    dist.all_gather(out_i, padded(idx_local, -1), group=group)
+    dist.all_gather(out_v, padded(val_local, float("-inf")), group=group)
+    return (torch.cat([t[:n] for t, n in zip(out_i, sizes)]), torch.cat([t[:n] for t, n in zip(out_v, sizes)]))

@@ -85,7 +85,8 @@ int eb_bpr_sample_philox(int32_t n_users, int32_t n_items,
 
 /* End-to-end variant of eb_bpr_step_f32 for HOST triples: copies the three
  * host index arrays into `staging` (device, 3*n int32), runs the step, copies
- * the loss back into *loss_host and synchronises the stream. */
+ * the loss back into *loss_host and synchronises the stream (flags bit1 = do NOT synchronise:
+ * lets the caller pipeline steps on two streams so the next batch's H2D overlaps this kernel). */
 int eb_bpr_step_host_f32(float *U, float *V, float *item_bias, int d, int ld,
                          const int32_t *tu_host, const int32_t *ti_host, const int32_t *tj_host, int64_t n,
                          float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
@@ -157,6 +158,25 @@ int eb_bpr_batch_grad_f32(const float *Gu, const float *Gi, const float *Bi, flo
                           float l_w, float l_b, double *loss, void *stream);
 int eb_adam_dense_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
                       float eps, int64_t step, void *stream);
+
+/* Multi-GPU reconciliation of a REPLICATED table (item factors / biases): every
+ * rank computes delta = cur - prev, the host all-reduces `delta` (NCCL), then
+ * cur = prev = prev + sum(delta).  No reference counterpart (the reference is single-device). */
+int eb_table_delta_f32(const float *cur, const float *prev, float *delta, int64_t n, void *stream);
+int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Dense layers (MultiVAE encoder/decoder, NeuMF MLP): bf16 tensor-core GEMM
+ *   C[M][N] (fp32) = act(alpha * A[M][K] . B[N][K]^T + bias[N])      act: 0 none, 1 tanh, 2 relu
+ * A and B are bf16 with K contiguous (Keras Dense kernels kept as [out][in]); replaces the
+ * tf.keras.layers.Dense calls of multi_vae_model.py:44-53,72-78 and
+ * neural_matrix_factorization_model.py:57-70.  eb_convert_bf16 produces the bf16 operand from an
+ * fp32 matrix, optionally transposed ([rows][cols] -> [cols][dst_ld]); dst_ld % 8 == 0.
+ * ------------------------------------------------------------------------ */
+int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld, void *dst_bf16, int64_t dst_ld, int transpose,
+                    void *stream);
+int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
+                    int M, int N, int K, const float *bias, float alpha, int act, void *stream);
 
 /* Tensor-core path (tcgen05 + TMEM + TMA, bf16 mainloop, exact fp32 re-rank).  Same contract and
  * same RESULT as eb_score_topk_f32 (identical index lists and scores): the kernel keeps the 32

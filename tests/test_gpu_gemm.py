@@ -1,0 +1,39 @@
+"""tcgen05 GEMM (dense layers of MultiVAE / NeuMF) vs a bf16-rounded fp64 matmul."""
+import pytest
+import torch
+
+from elliot_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 600, 26744), (512, 400, 600), (26744, 600, 512), (130, 70, 200), (1, 1, 8),
+                                  (257, 129, 1000), (600, 200, 512)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_matches_bf16_matmul(M, N, K, act):
+    if act and M * N * K > 3e9:
+        pytest.skip("activation variants on the small shapes only")
+    g = torch.Generator(device=DEV); g.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g) / K ** 0.5
+    B = torch.randn(N, K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    Ab, Bb = ops.to_bf16(A), ops.to_bf16(B)
+    C = ops.gemm_bf16_tn(Ab, Bb, M, N, K, bias=bias, alpha=0.5, act=act)
+    ref = 0.5 * (A.bfloat16().double() @ B.bfloat16().double().T) + bias.double()
+    if act == 1: ref = torch.tanh(ref)
+    if act == 2: ref = torch.relu(ref)
+    assert (C.double() - ref).abs().max().item() < 2e-4      # fp32 accumulation of <= 26744 products
+
+
+def test_convert_transpose_roundtrip():
+    g = torch.Generator(device=DEV); g.manual_seed(0)
+    X = torch.randn(301, 77, device=DEV, generator=g)
+    a = ops.to_bf16(X); t = ops.to_bf16(X, transpose=True)
+    assert a.shape == (301, 80) and t.shape == (77, 304)
+    assert torch.equal(a[:, :77], X.bfloat16()) and not a[:, 77:].any()
+    assert torch.equal(t[:, :301], X.bfloat16().T) and not t[:, 301:].any()
+    # GEMM on transposed operands: X^T X
+    C = ops.gemm_bf16_tn(t, t, 77, 77, 301)
+    ref = X.bfloat16().double().T @ X.bfloat16().double()
+    assert (C.double() - ref).abs().max().item() < 1e-3

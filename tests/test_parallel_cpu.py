@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard partition, replicated-table
+reconciliation protocol, user-sharded top-k gather."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from elliot_b200.parallel import ReplicatedTableSync, gather_topk, owner_of, shard_range
+
+
+def test_shard_range_partitions():
+    for n in [0, 1, 7, 8, 1000003]:
+        for w in [1, 2, 3, 8]:
+            rs = [shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+    for n, w in [(10, 3), (7, 2), (1000, 8)]:
+        for row in range(n):
+            r = owner_of(row, n, w)
+            lo, hi = shard_range(n, r, w)
+            assert lo <= row < hi
+
+
+def _worker(rank, world, init_file, out_dir):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    V = torch.randn(16, 8); b = torch.randn(16)
+    V0, b0 = V.clone(), b.clone()
+    sync = ReplicatedTableSync([V, b], delta_fn=lambda c, p, d: d.copy_(c - p),
+                               apply_fn=lambda c, p, s: (p.add_(s), c.copy_(p)))
+    for step in range(3):
+        # each rank touches different rows with different amounts (its local Hogwild step)
+        V[rank * 4 + step] += (rank + 1) * 0.5
+        V[15] += 0.25                                            # a row BOTH ranks touch
+        b[rank] -= 1.0
+        sync.sync()
+    want_V = V0.clone(); want_b = b0.clone()
+    for step in range(3):
+        for r in range(world):
+            want_V[r * 4 + step] += (r + 1) * 0.5
+            want_V[15] += 0.25
+            want_b[r] -= 1.0
+    ok = torch.allclose(V, want_V, atol=1e-6) and torch.allclose(b, want_b, atol=1e-6) and torch.equal(V, sync.prev[0])
+    # user-sharded top-k gather keeps user order
+    n_users = 11
+    lo, hi = shard_range(n_users, rank, world)
+    idx = torch.arange(lo, hi, dtype=torch.int32).unsqueeze(1).repeat(1, 3)
+    val = idx.float() * 0.5
+    gi, gv = gather_topk(idx, val, n_users)
+    ok = ok and torch.equal(gi[:, 0], torch.arange(n_users, dtype=torch.int32)) and torch.equal(gv, gi.float() * 0.5)
+    torch.save({"ok": ok, "V": V}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_replicated_table_sync_and_gather_world2():
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        init = os.path.join(d, "init")
+        mp.spawn(_worker, args=(world, init, d), nprocs=world, join=True)
+        res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
+    assert all(r["ok"] for r in res)
+    assert torch.equal(res[0]["V"], res[1]["V"])                  # replicas identical after every sync
