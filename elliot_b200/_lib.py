@@ -45,6 +45,14 @@ SIGNATURES = {
     "eb_convert_bf16": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_i64, c_int, c_void]),
     "eb_gemm_bf16_tn": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
                                 c_void]),
+    "eb_vae_embed_fwd": (c_int, [c_void, c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_i64, c_f32, c_u64, c_void]),
+    "eb_vae_embed_bwd": (c_int, [c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_i64, c_f32, c_u64, c_void]),
+    "eb_vae_reparam_fwd": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_i64, c_u64, c_u64, c_void, c_void]),
+    "eb_vae_reparam_bwd": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_i64, c_void, c_i64, c_u64, c_u64, c_f32, c_void]),
+    "eb_vae_softmax": (c_int, [c_void, c_i64, c_int, c_void, c_void, c_void, c_int, c_void, c_void, c_int, c_void]),
+    "eb_tanh_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
+    "eb_colsum": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_void]),
+    "eb_dense_topk_f32": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_void, c_void, c_void, c_int, c_void, c_void, c_void]),
     "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),

@@ -80,7 +80,7 @@ struct Rows {
 };
 
 template <int DP, bool SAMPLE, bool ATOMIC>
-__global__ void __launch_bounds__(256, 4) bpr_hogwild_kernel(const HogwildParams p) {
+__global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p) {
     constexpr int NV = DP / 4;                 // float4 per row
     constexpr int G = NV >= 32 ? 32 : NV;      // lanes per triple
     constexpr int VPL = NV / G;                // float4 per lane

@@ -263,3 +263,69 @@ def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
         check(lib().eb_gemm_bf16_tn(_ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(out), out.stride(0), M, N, K, _ptr(bias),
                                     alpha, act, _stream(A)))
     return out
+
+
+# ---------------------------------------------------------------- MultiVAE pieces (vae.cu)
+def vae_embed_fwd(W1, b1, indptr, indices, rows, h1, drop_rate=0.0, seed=0):
+    _need_cuda(W1, b1, indptr, indices, rows, h1)
+    with torch.cuda.device(W1.device):
+        check(lib().eb_vae_embed_fwd(_ptr(W1), _ptr(b1), W1.shape[1], _ptr(indptr), _ptr(indices), _ptr(rows), rows.numel(),
+                                     _ptr(h1), h1.stride(0), drop_rate, seed, _stream(W1)))
+
+
+def vae_embed_bwd(dW1, indptr, indices, rows, dpre1, drop_rate=0.0, seed=0):
+    _need_cuda(dW1, indptr, indices, rows, dpre1)
+    with torch.cuda.device(dW1.device):
+        check(lib().eb_vae_embed_bwd(_ptr(dW1), dW1.shape[1], _ptr(indptr), _ptr(indices), _ptr(rows), rows.numel(), _ptr(dpre1),
+                                     dpre1.stride(0), drop_rate, seed, _stream(dW1)))
+
+
+def vae_reparam_fwd(ml, L, z, seed, step, kl_sum=None):
+    _need_cuda(ml, z, kl_sum)
+    with torch.cuda.device(ml.device):
+        check(lib().eb_vae_reparam_fwd(_ptr(ml), ml.stride(0), ml.shape[0], L, _ptr(z), z.stride(0), seed, step, _ptr(kl_sum),
+                                       _stream(ml)))
+
+
+def vae_reparam_bwd(ml, L, dz, dml, seed, step, anneal):
+    _need_cuda(ml, dz, dml)
+    with torch.cuda.device(ml.device):
+        check(lib().eb_vae_reparam_bwd(_ptr(ml), ml.stride(0), ml.shape[0], L, _ptr(dz), dz.stride(0), _ptr(dml), dml.stride(0),
+                                       seed, step, anneal, _stream(ml)))
+
+
+def vae_softmax(logits, indptr, indices, rows, nll_sum=None, lse_out=None, write_grad=True):
+    _need_cuda(logits, indptr, indices, rows, nll_sum, lse_out)
+    with torch.cuda.device(logits.device):
+        check(lib().eb_vae_softmax(_ptr(logits), logits.stride(0), logits.shape[1], _ptr(indptr), _ptr(indices), _ptr(rows),
+                                   logits.shape[0], _ptr(nll_sum), _ptr(lse_out), 1 if write_grad else 0, _stream(logits)))
+
+
+def tanh_bwd(dout, out, dpre=None):
+    _need_cuda(dout, out, dpre)
+    assert dout.is_contiguous() and out.is_contiguous()
+    if dpre is None:
+        dpre = torch.empty_like(dout)
+    with torch.cuda.device(dout.device):
+        check(lib().eb_tanh_bwd(_ptr(dout), _ptr(out), _ptr(dpre), dout.numel(), _stream(dout)))
+    return dpre
+
+
+def colsum(src, out=None):
+    _need_cuda(src, out)
+    if out is None:
+        out = torch.empty(src.shape[1], dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().eb_colsum(_ptr(src), src.shape[0], src.shape[1], src.stride(0), _ptr(out), _stream(src)))
+    return out
+
+
+def dense_topk(scores, k, mask_indptr=None, mask_indices=None, rows=None, shift=None):
+    _need_cuda(scores, mask_indptr, mask_indices, rows, shift)
+    n = scores.shape[0]
+    idx = torch.empty((n, k), dtype=torch.int32, device=scores.device)
+    val = torch.empty((n, k), dtype=torch.float32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib().eb_dense_topk_f32(_ptr(scores), scores.stride(0), n, scores.shape[1], _ptr(mask_indptr), _ptr(mask_indices),
+                                      _ptr(rows), _ptr(shift), k, _ptr(idx), _ptr(val), _stream(scores)))
+    return idx, val

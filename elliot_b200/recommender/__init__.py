@@ -2,3 +2,4 @@
 (elliot/run.py:75, elliot/recommender/__init__.py)."""
 from .bprmf import BPRMF, MFModel  # noqa: F401
 from .bprmf_batch import BPRMF_batch, BPRMFBatchModel  # noqa: F401
+from .multi_vae import MultiVAE, VariationalAutoEncoder  # noqa: F401

@@ -159,6 +159,28 @@ int eb_bpr_batch_grad_f32(const float *Gu, const float *Gi, const float *Bi, flo
 int eb_adam_dense_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
                       float eps, int64_t step, void *stream);
 
+/* ------------------------------------------------------------------------
+ * MultiVAE pieces around the dense layers (multi_vae_model.py:20-159, sparse_sampler.py:13-25).
+ * rows[b] = private user id of batch row b; indptr/indices = train CSR (the dense B x I input of
+ * the reference is never materialised).  See elliot_b200/csrc/vae.cu for the per-call formulas.
+ * ------------------------------------------------------------------------ */
+int eb_vae_embed_fwd(const float *W1, const float *b1, int H, const int64_t *indptr, const int32_t *indices,
+                     const int32_t *rows, int B, float *h1, int64_t ldh, float drop_rate, uint64_t seed, void *stream);
+int eb_vae_embed_bwd(float *dW1, int H, const int64_t *indptr, const int32_t *indices, const int32_t *rows, int B,
+                     const float *dpre1, int64_t ldd, float drop_rate, uint64_t seed, void *stream);
+int eb_vae_reparam_fwd(const float *ml, int64_t ldml, int B, int L, float *z, int64_t ldz, uint64_t seed, uint64_t step,
+                       double *kl_sum, void *stream);
+int eb_vae_reparam_bwd(const float *ml, int64_t ldml, int B, int L, const float *dz, int64_t lddz, float *dml,
+                       int64_t lddml, uint64_t seed, uint64_t step, float anneal, void *stream);
+int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
+                   const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *stream);
+int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
+int eb_colsum(const float *src, int rows, int cols, int64_t ld, float *out, void *stream);
+/* masked top-k over an existing dense score block (scores are overwritten); out_val = score + shift[row] */
+int eb_dense_topk_f32(float *scores, int64_t ld, int n_rows, int n_items, const int64_t *mask_indptr,
+                      const int32_t *mask_indices, const int32_t *rows, const float *shift, int k, int32_t *out_idx,
+                      float *out_val, void *stream);
+
 /* Multi-GPU reconciliation of a REPLICATED table (item factors / biases): every
  * rank computes delta = cur - prev, the host all-reduces `delta` (NCCL), then
  * cur = prev = prev + sum(delta).  No reference counterpart (the reference is single-device). */

@@ -66,3 +66,40 @@ def glorot_uniform(rng, shape):
     cannot be replayed here)."""
     lim = np.sqrt(6.0 / (shape[0] + shape[1]))
     return rng.uniform(-lim, lim, size=shape)
+
+
+# ---------------------------------------------------------------- MultiVAE (parity unpinned)
+def multivae_forward_backward(P, X, eps, anneal):
+    """VariationalAutoEncoder.call/train_step, multi_vae_model.py:114-142, for a dense binary batch X
+    (B x I) and given reparametrisation noise eps (B x L).  P holds Keras-layout weights:
+    W1 (I x H), b1, W2 (H x 2L: dense_mean | dense_log_var), b2, W3 (L x H), b3, W4 (H x I), b4.
+    kernel_regularizer losses are declared but never added to the loss in the reference
+    (multi_vae_model.py:47-53,75-78 vs :136) -> reg_lambda is inert, as here.
+    Returns loss, grads dict, (logits, mu, lv, z)."""
+    B, L = eps.shape
+    nrm = np.sqrt((X ** 2).sum(1, keepdims=True)); nrm[nrm == 0] = 1.0
+    xh = X / nrm                                                  # l2_normalize, :42
+    h1 = np.tanh(xh @ P["W1"] + P["b1"])
+    ml = h1 @ P["W2"] + P["b2"]
+    mu, lv = ml[:, :L], ml[:, L:]
+    z = mu + np.exp(0.5 * lv) * eps                               # Sampling, :20-29
+    h2 = np.tanh(z @ P["W3"] + P["b3"])
+    logits = h2 @ P["W4"] + P["b4"]
+    m = logits.max(1, keepdims=True)
+    lse = m + np.log(np.exp(logits - m).sum(1, keepdims=True))
+    ls = logits - lse
+    kl = -0.5 * np.mean(lv - mu ** 2 - np.exp(lv) + 1)            # :119-121
+    neg_ll = -np.mean((ls * X).sum(1))                            # :131-135
+    loss = neg_ll + anneal * kl
+    dlogits = (np.exp(ls) * X.sum(1, keepdims=True) - X) / B
+    G = {"W4": h2.T @ dlogits, "b4": dlogits.sum(0)}
+    dpre2 = (dlogits @ P["W4"].T) * (1 - h2 ** 2)
+    G["W3"] = z.T @ dpre2; G["b3"] = dpre2.sum(0)
+    dz = dpre2 @ P["W3"].T
+    dmu = dz + anneal * mu / (B * L)
+    dlv = dz * 0.5 * np.exp(0.5 * lv) * eps + anneal * 0.5 * (np.exp(lv) - 1) / (B * L)
+    dml = np.concatenate([dmu, dlv], 1)
+    G["W2"] = h1.T @ dml; G["b2"] = dml.sum(0)
+    dpre1 = (dml @ P["W2"].T) * (1 - h1 ** 2)
+    G["W1"] = xh.T @ dpre1; G["b1"] = dpre1.sum(0)
+    return loss, G, (logits, mu, lv, z, neg_ll, kl)
