@@ -212,6 +212,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from elliot_b200 import ops
