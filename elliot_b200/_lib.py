@@ -53,6 +53,16 @@ SIGNATURES = {
     "eb_tanh_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_colsum": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_void]),
     "eb_dense_topk_f32": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_void, c_void, c_void, c_int, c_void, c_void, c_void]),
+    "eb_neumf_gather": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void]),
+    "eb_neumf_head": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_void, c_void, c_i64, c_void, c_void, c_void, c_void,
+                              c_void, c_void, c_void]),
+    "eb_relu_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
+    "eb_neumf_scatter": (c_int, [c_void, c_void, c_int, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_void,
+                                 c_void, c_void, c_void]),
+    "eb_neumf_sample": (c_int, [c_i32, c_i32, c_void, c_void, c_int, c_u64, c_i64, c_void, c_void, c_void, c_void]),
+    "eb_neumf_pair_h1": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_int, c_int, c_int, c_void, c_i64, c_void]),
+    "eb_neumf_pair_head": (c_int, [c_void, c_void, c_i64, c_int, c_int, c_int, c_int, c_void, c_i64, c_void, c_void, c_void, c_i64,
+                                   c_void]),
     "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),

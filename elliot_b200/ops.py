@@ -329,3 +329,55 @@ def dense_topk(scores, k, mask_indptr=None, mask_indices=None, rows=None, shift=
         check(lib().eb_dense_topk_f32(_ptr(scores), scores.stride(0), n, scores.shape[1], _ptr(mask_indptr), _ptr(mask_indices),
                                       _ptr(rows), _ptr(shift), k, _ptr(idx), _ptr(val), _stream(scores)))
     return idx, val
+
+
+# ---------------------------------------------------------------- NeuMF pieces (neumf.cu)
+def _call(name, dev_tensor, *args):
+    with torch.cuda.device(dev_tensor.device):
+        check(getattr(lib(), name)(*args, _stream(dev_tensor)))
+
+
+def neumf_gather(Umf, Imf, Umlp, Imlp, f, u, it, x0, pm):
+    _need_cuda(Umf, Imf, Umlp, Imlp, u, it, x0, pm)
+    _call("eb_neumf_gather", Umf, _ptr(Umf), _ptr(Imf), _ptr(Umlp), _ptr(Imlp), f, Umf.stride(0), _ptr(u), _ptr(it), u.numel(),
+          _ptr(x0), x0.stride(0), _ptr(pm), pm.stride(0))
+
+
+def neumf_head(pm, h3, f, wp, bp, label=None, dpm=None, dh3=None, dwp=None, dbp=None, loss=None, prob=None):
+    _need_cuda(pm, h3, wp, bp, label, dpm, dh3, dwp, dbp, loss, prob)
+    _call("eb_neumf_head", pm, _ptr(pm), pm.stride(0), _ptr(h3), h3.stride(0), f, _ptr(wp), _ptr(bp), _ptr(label), pm.shape[0],
+          _ptr(dpm), _ptr(dh3), _ptr(dwp), _ptr(dbp), _ptr(loss), _ptr(prob))
+
+
+def relu_bwd(dout, out):
+    _need_cuda(dout, out)
+    dpre = torch.empty_like(dout)
+    _call("eb_relu_bwd", dout, _ptr(dout), _ptr(out), _ptr(dpre), dout.numel())
+    return dpre
+
+
+def neumf_scatter(Umf, Imf, f, u, it, dpm, dx0, dUmf, dImf, dUmlp, dImlp):
+    _need_cuda(Umf, Imf, u, it, dpm, dx0, dUmf, dImf, dUmlp, dImlp)
+    _call("eb_neumf_scatter", Umf, _ptr(Umf), _ptr(Imf), f, Umf.stride(0), _ptr(u), _ptr(it), u.numel(), _ptr(dpm), dpm.stride(0),
+          _ptr(dx0), dx0.stride(0), _ptr(dUmf), _ptr(dImf), _ptr(dUmlp), _ptr(dImlp))
+
+
+def neumf_sample(n_users, n_items, indptr, indices, m, seed):
+    _need_cuda(indptr, indices)
+    total = int(indices.numel()) * (1 + m)
+    dev = indptr.device
+    u = torch.empty(total, dtype=torch.int32, device=dev); i = torch.empty_like(u)
+    y = torch.empty(total, dtype=torch.float32, device=dev)
+    _call("eb_neumf_sample", indptr, n_users, n_items, _ptr(indptr), _ptr(indices), m, seed, total, _ptr(u), _ptr(i), _ptr(y))
+    return u, i, y
+
+
+def neumf_pair_h1(Au, Ai, b1, n_ub, n_items, h1, out):
+    _need_cuda(Au, Ai, b1, out)
+    _call("eb_neumf_pair_h1", Au, _ptr(Au), Au.stride(0), _ptr(Ai), Ai.stride(0), _ptr(b1), n_ub, n_items, h1, _ptr(out), out.stride(0))
+
+
+def neumf_pair_head(Umf, Imf, f, u0, n_ub, n_items, h3, wp, bp, prob):
+    _need_cuda(Umf, Imf, h3, wp, bp, prob)
+    _call("eb_neumf_pair_head", Umf, _ptr(Umf), _ptr(Imf), Umf.stride(0), f, u0, n_ub, n_items, _ptr(h3), h3.stride(0), _ptr(wp),
+          _ptr(bp), _ptr(prob), prob.stride(0))

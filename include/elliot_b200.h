@@ -181,6 +181,26 @@ int eb_dense_topk_f32(float *scores, int64_t ld, int n_rows, int n_items, const 
                       const int32_t *mask_indices, const int32_t *rows, const float *shift, int k, int32_t *out_idx,
                       float *out_val, void *stream);
 
+/* ------------------------------------------------------------------------
+ * NeuMF pieces around the dense layers (neural_matrix_factorization_model.py:38-148,
+ * NeuMF/custom_sampler.py:27-48).  See elliot_b200/csrc/neumf.cu for the per-call formulas.
+ * ------------------------------------------------------------------------ */
+int eb_neumf_gather(const float *Umf, const float *Imf, const float *Umlp, const float *Imlp, int f, int64_t ldt,
+                    const int32_t *u, const int32_t *it, int64_t n, float *x0, int64_t ldx, float *pm, int64_t ldp, void *stream);
+int eb_neumf_head(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
+                  const float *label, int64_t n, float *dpm, float *dh3, float *dwp, float *dbp, double *loss,
+                  float *prob_out, void *stream);
+int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
+int eb_neumf_scatter(const float *Umf, const float *Imf, int f, int64_t ldt, const int32_t *u, const int32_t *it, int64_t n,
+                     const float *dpm, int64_t ldp, const float *dx0, int64_t ldx, float *dUmf, float *dImf, float *dUmlp,
+                     float *dImlp, void *stream);
+int eb_neumf_sample(int32_t n_users, int32_t n_items, const int64_t *indptr, const int32_t *indices, int m, uint64_t seed,
+                    int64_t total, int32_t *out_u, int32_t *out_i, float *out_label, void *stream);
+int eb_neumf_pair_h1(const float *Au, int64_t ldau, const float *Ai, int64_t ldai, const float *b1, int n_ub, int n_items,
+                     int h1, void *out_bf16, int64_t ldo, void *stream);
+int eb_neumf_pair_head(const float *Umf, const float *Imf, int64_t ldt, int f, int u0, int n_ub, int n_items, const float *h3,
+                       int64_t ldh, const float *wp, const float *bp, float *prob, int64_t ldpr, void *stream);
+
 /* Multi-GPU reconciliation of a REPLICATED table (item factors / biases): every
  * rank computes delta = cur - prev, the host all-reduces `delta` (NCCL), then
  * cur = prev = prev + sum(delta).  No reference counterpart (the reference is single-device). */

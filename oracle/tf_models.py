@@ -103,3 +103,37 @@ def multivae_forward_backward(P, X, eps, anneal):
     dpre1 = (dml @ P["W2"].T) * (1 - h1 ** 2)
     G["W1"] = xh.T @ dpre1; G["b1"] = dpre1.sum(0)
     return loss, G, (logits, mu, lv, z, neg_ll, kl)
+
+
+# ---------------------------------------------------------------- NeuMF (parity unpinned)
+def neumf_forward_backward(P, u, i, y):
+    """NeuralMatrixFactorizationModel.call/train_step (neural_matrix_factorization_model.py:74-106), dropout 0,
+    is_mf_train = is_mlp_train = True.  P: U_mf, I_mf, U_mlp, I_mlp (tables), W1 (2f x 4f), b1, W2 (4f x 2f), b2,
+    W3 (2f x f), b3, wp (2f), bp (scalar) in Keras layout.  Keras BinaryCrossentropy: mean over the batch of
+    -(y log p + (1-y) log(1-p)) with p clipped to [1e-7, 1-1e-7]."""
+    B = len(u)
+    x0 = np.concatenate([P["U_mlp"][u], P["I_mlp"][i]], 1)
+    pm = P["U_mf"][u] * P["I_mf"][i]
+    h1 = np.maximum(x0 @ P["W1"] + P["b1"], 0); h2 = np.maximum(h1 @ P["W2"] + P["b2"], 0)
+    h3 = np.maximum(h2 @ P["W3"] + P["b3"], 0)
+    feat = np.concatenate([pm, h3], 1)
+    logit = feat @ P["wp"] + P["bp"]
+    p = 1 / (1 + np.exp(-logit))
+    pc = np.clip(p, 1e-7, 1 - 1e-7)
+    loss = np.mean(-(y * np.log(pc) + (1 - y) * np.log(1 - pc)))
+    dl = np.where((p > 1e-7) & (p < 1 - 1e-7), p - y, 0.0) / B
+    f = pm.shape[1]
+    G = {"wp": feat.T @ dl, "bp": dl.sum()}
+    dpm = dl[:, None] * P["wp"][None, :f]
+    dpre3 = (dl[:, None] * P["wp"][None, f:]) * (h3 > 0)
+    G["W3"] = h2.T @ dpre3; G["b3"] = dpre3.sum(0)
+    dpre2 = (dpre3 @ P["W3"].T) * (h2 > 0)
+    G["W2"] = h1.T @ dpre2; G["b2"] = dpre2.sum(0)
+    dpre1 = (dpre2 @ P["W2"].T) * (h1 > 0)
+    G["W1"] = x0.T @ dpre1; G["b1"] = dpre1.sum(0)
+    dx0 = dpre1 @ P["W1"].T
+    for k in ("U_mf", "I_mf", "U_mlp", "I_mlp"):
+        G[k] = np.zeros_like(P[k])
+    np.add.at(G["U_mf"], u, dpm * P["I_mf"][i]); np.add.at(G["I_mf"], i, dpm * P["U_mf"][u])
+    np.add.at(G["U_mlp"], u, dx0[:, :f]); np.add.at(G["I_mlp"], i, dx0[:, f:])
+    return loss, G, p
