@@ -381,3 +381,10 @@ def neumf_pair_head(Umf, Imf, f, u0, n_ub, n_items, h3, wp, bp, prob):
     _need_cuda(Umf, Imf, h3, wp, bp, prob)
     _call("eb_neumf_pair_head", Umf, _ptr(Umf), _ptr(Imf), Umf.stride(0), f, u0, n_ub, n_items, _ptr(h3), h3.stride(0), _ptr(wp),
           _ptr(bp), _ptr(prob), prob.stride(0))
+
+
+def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local):
+    _need_cuda(cur, prev, delta_sum, delta_local)
+    with torch.cuda.device(cur.device):
+        check(lib().eb_table_apply_delta_late_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), _ptr(delta_local), cur.numel(),
+                                                  _stream(cur)))

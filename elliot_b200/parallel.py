@@ -48,6 +48,65 @@ class ReplicatedTableSync:
             self._apply(t, p, d)
 
 
+class OverlappedTableSync:
+    """Same reconciliation, one step late, so the all-reduce of step k overlaps the compute of step k+1
+    (Hogwild tolerates the extra staleness; nothing is lost or double counted):
+
+        after step k  :  local_k = T - T_prev        (compute stream);  all_reduce(copy of local_k) on the comm stream
+        after step k+1:  wait for that all-reduce;  T += sum_k - local_k;  T_prev += sum_k;  then start round k+1
+
+    delta_fn / late_fn default to the CUDA kernels; CPU tests inject torch equivalents.
+    """
+
+    def __init__(self, tables, group=None, delta_fn=None, late_fn=None, stream=None):
+        from . import ops
+        self.tables = list(tables)
+        self.prev = [t.clone() for t in self.tables]
+        self.local = [torch.zeros_like(t) for t in self.tables]
+        self.sum = [torch.zeros_like(t) for t in self.tables]
+        self.group = group
+        self._delta = delta_fn or ops.table_delta_f32
+        self._late = late_fn or ops.table_apply_delta_late_f32
+        self.cuda = self.tables[0].is_cuda
+        self.comm = stream if stream is not None else (torch.cuda.Stream(device=self.tables[0].device) if self.cuda else None)
+        self.pending = False
+        self.ready = torch.cuda.Event() if self.cuda else None
+        self.done = torch.cuda.Event() if self.cuda else None
+
+    def _finish(self):
+        if not self.pending:
+            return
+        if self.cuda:
+            torch.cuda.current_stream(self.tables[0].device).wait_event(self.done)
+        for t, p, s, l in zip(self.tables, self.prev, self.sum, self.local):
+            self._late(t, p, s, l)
+        self.pending = False
+
+    def sync(self):
+        """Call once after every local step."""
+        self._finish()                                       # apply round k-1 (other ranks' updates arrive one step late)
+        for t, p, l, s in zip(self.tables, self.prev, self.local, self.sum):
+            self._delta(t, p, l)
+            s.copy_(l)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if self.cuda:
+            self.ready.record()
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ready)
+                if world > 1:
+                    for s in self.sum:
+                        dist.all_reduce(s, group=self.group)
+                self.done.record()
+        elif world > 1:
+            for s in self.sum:
+                dist.all_reduce(s, group=self.group)
+        self.pending = True
+
+    def flush(self):
+        """Apply the outstanding round (end of training / before scoring)."""
+        self._finish()
+
+
 def gather_topk(idx_local, val_local, n_users, group=None):
     """Concatenate user-sharded (idx, val) blocks in rank order (block partition => user order).
     Shards may differ by one row: blocks are padded to the largest shard for the all_gather."""

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from elliot_b200.parallel import ReplicatedTableSync, gather_topk, owner_of, shard_range
+from elliot_b200.parallel import OverlappedTableSync, ReplicatedTableSync, gather_topk, owner_of, shard_range
 
 
 def test_shard_range_partitions():
@@ -53,6 +53,21 @@ def _worker(rank, world, init_file, out_dir):
     val = idx.float() * 0.5
     gi, gv = gather_topk(idx, val, n_users)
     ok = ok and torch.equal(gi[:, 0], torch.arange(n_users, dtype=torch.int32)) and torch.equal(gv, gi.float() * 0.5)
+    # overlapped (one-step-late) variant: after flush() the replicas agree and nothing is lost or doubled
+    W = torch.zeros(8, 4)
+    osync = OverlappedTableSync([W], delta_fn=lambda c, p, d: d.copy_(c - p),
+                                late_fn=lambda c, p, s, l: (c.add_(s - l), p.add_(s)))
+    for step in range(4):
+        W[rank + step] += 1.0 + rank
+        W[7] += 0.5
+        osync.sync()
+    osync.flush()
+    want_W = torch.zeros(8, 4)
+    for step in range(4):
+        for r in range(world):
+            want_W[r + step] += 1.0 + r
+            want_W[7] += 0.5
+    ok = ok and torch.allclose(W, want_W, atol=1e-6) and torch.allclose(osync.prev[0], want_W, atol=1e-6)
     torch.save({"ok": ok, "V": V}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
