@@ -161,13 +161,23 @@ constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 colu
 
 template <int KP> struct TcCfg {
     static constexpr int KB = KP / 64;                       // 64-wide K blocks (one swizzle atom each)
-    static constexpr int BN = KP <= 128 ? 256 : (KP == 192 ? 128 : 64);   // items per tile (UMMA N)
-    static constexpr int STAGES = KP == 64 ? 3 : 2;
+    // Epilogue warpgroups.  NG = 2 (tile-parity split, two candidate lists per row merged per user block) is
+    // implemented and exact, but measured no faster than NG = 1 on B200: each half-stream has a lower threshold
+    // (1.85x more inserts) and the smaller B tiles it forces cost more than the extra warps gain.
+    static constexpr int NG = 1;
+    static constexpr int BN = NG == 2 ? (KP == 64 ? 256 : (KP == 128 ? 128 : 64))
+                                      : (KP <= 128 ? 256 : (KP == 192 ? 128 : 64));   // items per tile (UMMA N)
+    static constexpr int STAGES = (NG == 1 && KP == 64) ? 3 : 2;
+    static constexpr int THREADS = 64 + 128 * NG;            // TMA warp + MMA warp + NG x 4 epilogue warps
     static constexpr int A_BYTES = TC_BM * KP * 2;
     static constexpr int B_BYTES = BN * KP * 2;
-    static constexpr int CAND_BYTES = TC_BM * TC_BUF * 8;
-    static constexpr int SMEM = A_BYTES + STAGES * B_BYTES + CAND_BYTES + 256;
+    static constexpr int CAND_BYTES = NG * TC_BM * TC_BUF * 8;
+    static constexpr int SMEM = A_BYTES + STAGES * B_BYTES + CAND_BYTES + 1024 /*merged cnt/thresh*/ + 256;
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
@@ -249,16 +259,16 @@ __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint
 }
 
 template <int KP, bool DUMP, bool HAS_BIAS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<KP>::THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using C = TcCfg<KP>;
-    constexpr int KB = C::KB, BN = C::BN, S = C::STAGES;
+    constexpr int KB = C::KB, BN = C::BN, S = C::STAGES, NG = C::NG;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
     uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
     const uint32_t cval = smem_u32(sB + S * C::B_BYTES);                     // float [BUF][128]
-    const uint32_t cidx = cval + TC_BUF * TC_BM * 4;                         // int   [BUF][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + S * C::B_BYTES + C::CAND_BYTES);
+    const uint32_t mrg = cval + C::CAND_BYTES;                               // merged per-row {cnt[128], thresh[128]}
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + S * C::B_BYTES + C::CAND_BYTES + 1024);
     const uint32_t bar0 = smem_u32(bars);
     auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(S + s); };
@@ -333,16 +343,22 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else {
-        // ===================== epilogue: warps 2..5 =====================
+        // ===================== epilogue: warps 2..5 (group 0) and, if NG == 2, warps 6..9 (group 1) =====================
+        // Group g owns TMEM accumulator g, i.e. the tiles with (global tile counter & 1) == g, and its own candidate
+        // buffers; the two per-row lists are merged at the end of every user block.
+        const int grp = NG == 2 ? ((warp - 2) >> 2) : 0;
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;             // row inside the 128-user block
         const float NEG = -CUDART_INF_F;
         // candidate buffer: row-major [128 rows][64 slots] of sortable keys + item ids; logical slot s of row r
         // lives at physical position (s + r) & 63 (rotation: conflict-free appends AND conflict-free row reads)
-        const uint32_t ckey = cval;                   // uint32 keys
+        const uint32_t ckey = cval + (uint32_t)grp * (TC_BM * TC_BUF * 8);   // uint32 keys [128][64], then ids [128][64]
+        const uint32_t cidx = ckey + TC_BM * TC_BUF * 4;
+        const uint32_t ckey0 = cval, cidx0 = cval + TC_BM * TC_BUF * 4;       // group 0's buffers hold the merged lists
         uint32_t tile = 0;
         long long c_wait = 0, c_ld = 0, c_scan = 0, c_comp = 0, c_rank = 0, n_comp = 0, n_slow = 0, n_grp = 0;
         const bool prof = p.prof != nullptr && warp == 2;
+        constexpr int EPI_THREADS = 128 * NG;
         for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x) {
             const int q = mb * TC_BM + row;           // position in the selected user range
             const bool valid = q < p.n_sel;
@@ -364,6 +380,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
             for (int t = 0; t < n_tiles; t++, tile++) {
                 const int acc = tile & 1;
+                if (NG == 2 && acc != grp) continue;
                 long long t0 = prof ? clock64() : 0;
                 mbar_wait(ACC_FULL(acc), (tile >> 1) & 1);
                 tc_fence_after();
@@ -404,32 +421,36 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         n_grp++;
                         const uint32_t todo = __ballot_sync(0xffffffffu, cnt > TC_BUF - TC_SLACK);
                         if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > TC_BUF - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
-                        // branch-free append of the group's survivors: predicates first, exclusive prefix of the
-                        // predicates gives each survivor its slot (no serial dependency through cnt)
-                        float sc[8]; uint32_t tk[8]; int ofs[8];
+                        // Append survivors one at a time, largest first: locate the group's max with static
+                        // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
+                        // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
+                        float w8[8];
 #pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            const int cc = s8 * 8 + c;
-                            sc[c] = HAS_BIAS ? v[cc] + __ldg(p.bias + min(col0 + cc, p.n_items - 1)) : v[cc];
-                            tk[c] = sc[c] > thresh ? 1u : 0u;
-                        }
-                        ofs[0] = 0;
+                        for (int c = 0; c < 8; c++)
+                            w8[c] = HAS_BIAS ? v[s8 * 8 + c] + __ldg(p.bias + min(col0 + s8 * 8 + c, p.n_items - 1)) : v[s8 * 8 + c];
+                        float gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
+#pragma unroll 1
+                        for (int round = 0; round < 8; round++) {
+                            if (!__any_sync(0xffffffffu, gm > thresh)) break;
+                            int am = 7;
 #pragma unroll
-                        for (int c = 1; c < 8; c++) ofs[c] = ofs[c - 1] + (int)tk[c - 1];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {
-                            const int pos = (cnt + ofs[c] + row) & 63;
-                            const uint32_t key = tc_key_of(sc[c], pos);
+                            for (int c = 6; c >= 0; c--) am = (w8[c] == gm) ? c : am;      // first position holding the max
+                            const uint32_t take = gm > thresh ? 1u : 0u;
+                            const int pos = (cnt + row) & 63;
+                            const uint32_t key = tc_key_of(gm, pos);
                             asm volatile(
                                 "{\n\t.reg .pred p;\n\t"
                                 "setp.ne.u32 p, %0, 0;\n\t"
                                 "@p st.shared.u32 [%1], %2;\n\t"
                                 "@p st.shared.s32 [%3], %4;\n\t}"
-                                ::"r"(tk[c]), "r"(my_key + 4u * (uint32_t)pos), "r"(key), "r"(my_idx + 4u * (uint32_t)pos),
-                                  "r"(col0 + s8 * 8 + c)
+                                ::"r"(take), "r"(my_key + 4u * (uint32_t)pos), "r"(key), "r"(my_idx + 4u * (uint32_t)pos),
+                                  "r"(col0 + s8 * 8 + am)
                                 : "memory");
+                            cnt += (int)take;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) w8[c] = (take && c == am) ? -CUDART_INF_F : w8[c];
+                            gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
                         }
-                        cnt += ofs[7] + (int)tk[7];
                     }
                     if (prof) c_scan += clock64() - t2;
                 }
@@ -441,20 +462,48 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
             long long t4 = prof ? clock64() : 0;
             compact(__ballot_sync(0xffffffffu, valid));
+            if (NG == 2) {
+                // ---- merge the two groups' lists into group 0's buffer
+                if (grp == 1) sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);      // partner threshold, read by group 0
+                named_bar_sync(1, EPI_THREADS);
+                if (grp == 0) {
+                    const uint32_t pkey = cval + TC_BM * TC_BUF * 8, pidx = pkey + TC_BM * TC_BUF * 4;
+                    for (int r = 0; r < 32; r++) {
+                        const int rrow = quad * 32 + r;
+                        const uint32_t src = 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63);
+                        const int dpos = (32 + lane + rrow) & 63;
+                        const uint32_t dst = 256u * (uint32_t)rrow + 4u * (uint32_t)dpos;
+                        const uint32_t k = (uint32_t)lds_s32(pkey + src);
+                        sts_s32(ckey0 + dst, (int)((k & ~63u) | (uint32_t)(63 - dpos)));
+                        sts_s32(cidx0 + dst, lds_s32(pidx + src));
+                    }
+                    __syncwarp();
+                    const float tp = lds_f32(mrg + 512u + 4u * (uint32_t)row);
+                    compact(__ballot_sync(0xffffffffu, valid));
+                    thresh = fmaxf(thresh, tp);                 // everything either group ever dropped is <= thresh
+                    sts_s32(mrg + 4u * (uint32_t)row, cnt);
+                    sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);
+                }
+                named_bar_sync(2, EPI_THREADS);
+            } else {
+                sts_s32(mrg + 4u * (uint32_t)row, cnt);
+                sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);
+                __syncwarp();
+            }
 
             const float vmax_n = p.vstat[0], bmax_a = p.vstat[1];
             const float my_unorm = valid ? p.unorm[q] : 0.f;
-            // ---- exact re-rank of this warp's 32 rows: lane l re-scores candidate l of the row in fp32 with the
+            // ---- exact re-rank (rows split between the groups): lane l re-scores candidate l of the row in fp32 with the
             // SAME operation order as score_topk.cu (32 strided partial sums, then the xor-butterfly tree)
-            for (int r = 0; r < 32; r++) {
+            for (int r = (NG == 2 ? grp * 16 : 0); r < (NG == 2 ? grp * 16 + 16 : 32); r++) {
                 const int rrow = quad * 32 + r;
                 const int rq = mb * TC_BM + rrow;
                 if (rq >= p.n_sel) break;                                 // warp-uniform
                 const int ru = p.user_begin + rq;
-                const int rcount = __shfl_sync(0xffffffffu, cnt, r);
-                const float rthresh = __shfl_sync(0xffffffffu, thresh, r);
+                const int rcount = lds_s32(mrg + 4u * (uint32_t)rrow);
+                const float rthresh = lds_f32(mrg + 512u + 4u * (uint32_t)rrow);
                 const bool have = lane < rcount;
-                const int my_i = have ? lds_s32(cidx + 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63)) : 0x7fffffff;
+                const int my_i = have ? lds_s32(cidx0 + 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63)) : 0x7fffffff;
                 float my_v = NEG;
                 if (have) {
                     const float *ur = p.U + (int64_t)ru * p.ld;
@@ -514,6 +563,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
             }
             __syncwarp();
+            if (NG == 2) named_bar_sync(3, EPI_THREADS);      // group 0's buffer is free for the next user block
             if (prof) c_rank += clock64() - t4;
         }
         if (prof && lane == 0 && blockIdx.x == 0) {
@@ -622,7 +672,7 @@ static int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const TcParams
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP>::SMEM));
     int grid = sm_count();
     if (grid > n_mblocks) grid = n_mblocks;
-    kern<<<grid, TC_THREADS, TcCfg<KP>::SMEM, st>>>(a, b, p);
+    kern<<<grid, TcCfg<KP>::THREADS, TcCfg<KP>::SMEM, st>>>(a, b, p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
@@ -679,7 +729,7 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     if (item_bias) tc_bias_kernel<<<((n_items + 31) / 32 + 255) / 256, 256, 0, st>>>(item_bias, n_items, bmax, vstat + 1);
     EB_CUDA(cudaGetLastError());
     CUtensorMap ma, mb;
-    const int BN = L.KP <= 128 ? 256 : (L.KP == 192 ? 128 : 64);
+    const int BN = L.KP <= 128 ? 256 : (L.KP == 192 ? 128 : 64);     // must equal TcCfg<KP>::BN
     if (int rc = make_map(&ma, ubf, (uint64_t)n_sel, L.KP, TC_BM)) return rc;
     if (int rc = make_map(&mb, vbf, (uint64_t)n_items, L.KP, BN)) return rc;
     TcParams p{};
