@@ -119,74 +119,77 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                 u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
             }
         }
-        int cu = __shfl_sync(0xffffffffu, u, gbase), ci = __shfl_sync(0xffffffffu, i, gbase),
-            cj = __shfl_sync(0xffffffffu, j, gbase);
-        Rows<VPL> cur;
-        load_rows(cur, cu, ci, cj);
+        // UNR triples of the group in flight at once: all their row loads are issued before the first reduction
+        constexpr int UNR = G >= 4 ? 4 : G;
+#pragma unroll 1
+        for (int s0 = 0; s0 < G; s0 += UNR) {
+            Rows<VPL> rw[UNR];
+            int tu_[UNR], ti_[UNR], tj_[UNR];
 #pragma unroll
-        for (int s = 0; s < G; s++) {
-            Rows<VPL> nxt;
-            int nu = -1, ni = 0, nj = 0;
-            if (s + 1 < G) {
-                nu = __shfl_sync(0xffffffffu, u, gbase + s + 1);
-                ni = __shfl_sync(0xffffffffu, i, gbase + s + 1);
-                nj = __shfl_sync(0xffffffffu, j, gbase + s + 1);
-                load_rows(nxt, nu, ni, nj);
-            }
-            // ---- score: x = (b_i - b_j) + U[u].(V_i - V_j)
-            float part = 0.f;
-            if (cu >= 0) {
-#pragma unroll
-                for (int v = 0; v < VPL; v++) {
-                    part += cur.u[v].x * (cur.vi[v].x - cur.vj[v].x) + cur.u[v].y * (cur.vi[v].y - cur.vj[v].y) +
-                            cur.u[v].z * (cur.vi[v].z - cur.vj[v].z) + cur.u[v].w * (cur.vi[v].w - cur.vj[v].w);
-                }
+            for (int q = 0; q < UNR; q++) {
+                tu_[q] = __shfl_sync(0xffffffffu, u, gbase + s0 + q);
+                ti_[q] = __shfl_sync(0xffffffffu, i, gbase + s0 + q);
+                tj_[q] = __shfl_sync(0xffffffffu, j, gbase + s0 + q);
+                load_rows(rw[q], tu_[q], ti_[q], tj_[q]);
             }
 #pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (cu >= 0) {
-                const float x = part + (cur.bi - cur.bj);
-                const float z = __fdividef(1.f, 1.f + __expf(x));  // BPRMF_model.py:98
-                if (gl == 0) loss_acc += fmaxf(-x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
-                float *pu = p.U + (int64_t)cu * ld, *pi = p.V + (int64_t)ci * ld, *pj = p.V + (int64_t)cj * ld;
+            for (int q = 0; q < UNR; q++) {
+                const Rows<VPL> &cur = rw[q];
+                const int cu = tu_[q], ci = ti_[q], cj = tj_[q];
+                // ---- score: x = (b_i - b_j) + U[u].(V_i - V_j)
+                float part = 0.f;
+                if (cu >= 0) {
 #pragma unroll
-                for (int v = 0; v < VPL; v++) {
-                    const float4 a = cur.u[v], bi4 = cur.vi[v], bj4 = cur.vj[v];
-                    float4 du, di, dj, un;
-                    du.x = p.lr * ((bi4.x - bj4.x) * z - p.reg_u * a.x);
-                    du.y = p.lr * ((bi4.y - bj4.y) * z - p.reg_u * a.y);
-                    du.z = p.lr * ((bi4.z - bj4.z) * z - p.reg_u * a.z);
-                    du.w = p.lr * ((bi4.w - bj4.w) * z - p.reg_u * a.w);
-                    un.x = a.x + du.x; un.y = a.y + du.y; un.z = a.z + du.z; un.w = a.w + du.w;
-                    // item rows see the UPDATED user row (view aliasing, BPRMF_model.py:92,109-116)
-                    di.x = p.lr * (un.x * z - p.reg_pos * bi4.x);
-                    di.y = p.lr * (un.y * z - p.reg_pos * bi4.y);
-                    di.z = p.lr * (un.z * z - p.reg_pos * bi4.z);
-                    di.w = p.lr * (un.w * z - p.reg_pos * bi4.w);
-                    dj.x = p.lr * (-un.x * z - p.reg_neg * bj4.x);
-                    dj.y = p.lr * (-un.y * z - p.reg_neg * bj4.y);
-                    dj.z = p.lr * (-un.z * z - p.reg_neg * bj4.z);
-                    dj.w = p.lr * (-un.w * z - p.reg_neg * bj4.w);
-                    const int e = (v * G + gl) * 4;
-                    if (ATOMIC) {
-                        red_add_v4(pu + e, du);
-                        red_add_v4(pi + e, di);
-                        red_add_v4(pj + e, dj);
-                    } else {
-                        *reinterpret_cast<float4 *>(pu + e) = un;
-                        *reinterpret_cast<float4 *>(pi + e) =
-                            make_float4(bi4.x + di.x, bi4.y + di.y, bi4.z + di.z, bi4.w + di.w);
-                        *reinterpret_cast<float4 *>(pj + e) =
-                            make_float4(bj4.x + dj.x, bj4.y + dj.y, bj4.z + dj.z, bj4.w + dj.w);
+                    for (int v = 0; v < VPL; v++) {
+                        part += cur.u[v].x * (cur.vi[v].x - cur.vj[v].x) + cur.u[v].y * (cur.vi[v].y - cur.vj[v].y) +
+                                cur.u[v].z * (cur.vi[v].z - cur.vj[v].z) + cur.u[v].w * (cur.vi[v].w - cur.vj[v].w);
                     }
                 }
-                if (gl == 0) {
-                    const float dbi = p.lr * (z - p.reg_b * cur.bi), dbj = p.lr * (-z - p.reg_b * cur.bj);
-                    if (ATOMIC) { red_add_f32(p.b + ci, dbi); red_add_f32(p.b + cj, dbj); }
-                    else { p.b[ci] = cur.bi + dbi; p.b[cj] = cur.bj + dbj; }
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (cu >= 0) {
+                    const float x = part + (cur.bi - cur.bj);
+                    const float z = __fdividef(1.f, 1.f + __expf(x));  // BPRMF_model.py:98
+                    if (gl == 0) loss_acc += fmaxf(-x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
+                    float *pu = p.U + (int64_t)cu * ld, *pi = p.V + (int64_t)ci * ld, *pj = p.V + (int64_t)cj * ld;
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        const float4 a = cur.u[v], bi4 = cur.vi[v], bj4 = cur.vj[v];
+                        float4 du, di, dj, un;
+                        du.x = p.lr * ((bi4.x - bj4.x) * z - p.reg_u * a.x);
+                        du.y = p.lr * ((bi4.y - bj4.y) * z - p.reg_u * a.y);
+                        du.z = p.lr * ((bi4.z - bj4.z) * z - p.reg_u * a.z);
+                        du.w = p.lr * ((bi4.w - bj4.w) * z - p.reg_u * a.w);
+                        un.x = a.x + du.x; un.y = a.y + du.y; un.z = a.z + du.z; un.w = a.w + du.w;
+                        // item rows see the UPDATED user row (view aliasing, BPRMF_model.py:92,109-116)
+                        di.x = p.lr * (un.x * z - p.reg_pos * bi4.x);
+                        di.y = p.lr * (un.y * z - p.reg_pos * bi4.y);
+                        di.z = p.lr * (un.z * z - p.reg_pos * bi4.z);
+                        di.w = p.lr * (un.w * z - p.reg_pos * bi4.w);
+                        dj.x = p.lr * (-un.x * z - p.reg_neg * bj4.x);
+                        dj.y = p.lr * (-un.y * z - p.reg_neg * bj4.y);
+                        dj.z = p.lr * (-un.z * z - p.reg_neg * bj4.z);
+                        dj.w = p.lr * (-un.w * z - p.reg_neg * bj4.w);
+                        const int e = (v * G + gl) * 4;
+                        if (ATOMIC) {
+                            red_add_v4(pu + e, du);
+                            red_add_v4(pi + e, di);
+                            red_add_v4(pj + e, dj);
+                        } else {
+                            *reinterpret_cast<float4 *>(pu + e) = un;
+                            *reinterpret_cast<float4 *>(pi + e) =
+                                make_float4(bi4.x + di.x, bi4.y + di.y, bi4.z + di.z, bi4.w + di.w);
+                            *reinterpret_cast<float4 *>(pj + e) =
+                                make_float4(bj4.x + dj.x, bj4.y + dj.y, bj4.z + dj.z, bj4.w + dj.w);
+                        }
+                    }
+                    if (gl == 0) {
+                        const float dbi = p.lr * (z - p.reg_b * cur.bi), dbj = p.lr * (-z - p.reg_b * cur.bj);
+                        if (ATOMIC) { red_add_f32(p.b + ci, dbi); red_add_f32(p.b + cj, dbj); }
+                        else { p.b[ci] = cur.bi + dbi; p.b[cj] = cur.bj + dbj; }
+                    }
                 }
             }
-            if (s + 1 < G) { cur = nxt; cu = nu; ci = ni; cj = nj; }
         }
     }
     if (p.loss) {
