@@ -43,52 +43,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region with NVML from a thread (2 ms period);
+    nvidia-smi -lms is too coarse for a 20 ms region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
-        self.idx = gpu_index
+        self.idx, self.sm, self.reasons, self.stop_flag, self.th, self.mx, self.err = gpu_index, [], set(), False, None, None, None
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as e:                      # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+        t0 = time.time()
+        while not self.sm and self.err is None and time.time() - t0 < 2.0:
+            time.sleep(0.005)                       # first sample taken before the timed region starts
+
+    def mark(self):
+        """Call right before the timed region: samples before this index are ignored."""
+        self.first = len(self.sm)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().strip().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=2)
+        sm = self.sm[getattr(self, "first", 0):]
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        hi = [x for x in sm if x >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no samples" + (f": {self.err}" if self.err else "")]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def synth_csr(torch, dev, seed):
@@ -262,6 +263,7 @@ def main():
     ke = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    clocks.mark()
     e0.record()
     for k in range(K):
         ks[k].record(); step(); ke[k].record()
