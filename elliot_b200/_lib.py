@@ -63,6 +63,10 @@ SIGNATURES = {
     "eb_neumf_pair_h1": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_int, c_int, c_int, c_void, c_i64, c_void]),
     "eb_neumf_pair_head": (c_int, [c_void, c_void, c_i64, c_int, c_int, c_int, c_int, c_void, c_i64, c_void, c_void, c_void, c_i64,
                                    c_void]),
+    "eb_gather_rows_f32": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_i64, c_void]),
+    "eb_scatter_add_rows_f32": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_i64, c_void]),
+    "eb_bpr_step_rows_f32": (c_int, [c_void, c_i64, c_void, c_void, c_void, c_i64, c_i64, c_int, c_f32, c_f32, c_f32, c_f32, c_f32,
+                                     c_void, c_void, c_void, c_void]),
     "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_late_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_void]),

@@ -388,3 +388,28 @@ def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local):
     with torch.cuda.device(cur.device):
         check(lib().eb_table_apply_delta_late_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), _ptr(delta_local), cur.numel(),
                                                   _stream(cur)))
+
+
+# ---------------------------------------------------------------- row-sharded tables (sharded.cu)
+def gather_rows_f32(table, ids, width=None, out=None):
+    _need_cuda(table, ids, out); _chk_idx(ids)
+    width = width or table.shape[1]
+    if out is None:
+        out = torch.empty((ids.numel(), table.stride(0)), dtype=torch.float32, device=table.device)
+    _call("eb_gather_rows_f32", table, _ptr(table), table.stride(0), _ptr(ids), ids.numel(), width, _ptr(out), out.stride(0))
+    return out
+
+
+def scatter_add_rows_f32(table, ids, rows, width=None):
+    _need_cuda(table, ids, rows); _chk_idx(ids)
+    width = width or table.shape[1]
+    _call("eb_scatter_add_rows_f32", table, _ptr(table), table.stride(0), _ptr(ids), ids.numel(), width, _ptr(rows), rows.stride(0))
+
+
+def bpr_step_rows_f32(U, tu, Ri, Rj, bias_col, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None):
+    """BPR update against fetched item rows; returns (dRi, dRj) deltas to send back to the owners."""
+    _need_cuda(U, tu, Ri, Rj, loss); _chk_idx(tu)
+    dRi, dRj = torch.empty_like(Ri), torch.empty_like(Rj)
+    _call("eb_bpr_step_rows_f32", U, _ptr(U), U.stride(0), _ptr(tu), _ptr(Ri), _ptr(Rj), Ri.stride(0), tu.numel(), bias_col,
+          lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(dRi), _ptr(dRj), _ptr(loss))
+    return dRi, dRj

@@ -107,6 +107,79 @@ class OverlappedTableSync:
         self._finish()
 
 
+class ShardedTable:
+    """A table whose rows are block-partitioned over the ranks (`shard_range`).  `fetch(ids)` returns copies of
+    arbitrary global rows (ids all-to-all -> owners gather -> rows all-to-all), `push(deltas)` sends per-row
+    deltas for the ids of the last fetch back to their owners, which add them into their shard.
+
+    gather_fn(local_table, local_ids) -> rows and scatter_fn(local_table, local_ids, rows) default to the CUDA
+    kernels (ops.gather_rows_f32 / ops.scatter_add_rows_f32); CPU tests inject torch equivalents.
+    Index bookkeeping (owner lookup, sort by owner, split sizes) uses torch ops: plumbing, no arithmetic on rows.
+    """
+
+    def __init__(self, n_rows, local, group=None, gather_fn=None, scatter_fn=None):
+        from . import ops
+        self.n_rows, self.local, self.group = n_rows, local, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lo, self.hi = shard_range(n_rows, self.rank, self.world)
+        assert local.shape[0] == self.hi - self.lo
+        self.bounds = torch.tensor([shard_range(n_rows, r, self.world)[1] for r in range(self.world)],
+                                   dtype=torch.int64, device=local.device)
+        self._gather = gather_fn or (lambda t, i: ops.gather_rows_f32(t, i))
+        self._scatter = scatter_fn or (lambda t, i, r: ops.scatter_add_rows_f32(t, i, r))
+        self._plan = None
+
+    def _exchange(self, send, send_counts, recv_counts):
+        out = torch.empty((int(sum(recv_counts)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        if self.world == 1:
+            out.copy_(send)
+        else:
+            dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                                   group=self.group)
+        return out
+
+    def fetch(self, ids):
+        """ids: int32 global row ids (any order, duplicates allowed) -> rows [len(ids), ld] in the same order."""
+        ids64 = ids.to(torch.int64)
+        owner = torch.searchsorted(self.bounds, ids64, right=True)
+        order = torch.argsort(owner, stable=True)
+        sorted_ids = ids64[order]
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        if self.world == 1:
+            recv_counts.copy_(send_counts)
+        else:
+            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        wanted = self._exchange(sorted_ids, sc, rc)                               # ids other ranks want from me
+        local_ids = (wanted - self.lo).to(torch.int32)
+        rows_out = self._gather(self.local, local_ids)                            # owners gather
+        rows_in = self._exchange(rows_out, rc, sc)                                # rows come back, grouped by owner
+        inv = torch.empty_like(order); inv[order] = torch.arange(order.numel(), device=order.device)
+        self._plan = (order, sc, rc, local_ids)
+        return rows_in[inv]
+
+    def push(self, deltas):
+        """deltas[t] is added to global row ids[t] of the last fetch (duplicates accumulate)."""
+        order, sc, rc, local_ids = self._plan
+        back = self._exchange(deltas[order].contiguous(), sc, rc)
+        self._scatter(self.local, local_ids, back)
+
+
+def sharded_bpr_step(U_local, items: "ShardedTable", tu_local, ti, tj, hyper, bias_col=-1, loss=None, step_fn=None):
+    """One BPR step with row-sharded ITEM tables: this rank's triples use local user rows
+    (tu_local = local row index) and global item ids; pos/neg item rows are fetched from their owners, the update
+    runs locally (ops.bpr_step_rows_f32), the item deltas go back to the owners."""
+    from . import ops
+    n = tu_local.numel()
+    rows = items.fetch(torch.cat([ti, tj]))
+    Ri, Rj = rows[:n].contiguous(), rows[n:].contiguous()
+    fn = step_fn or ops.bpr_step_rows_f32
+    dRi, dRj = fn(U_local, tu_local, Ri, Rj, bias_col, *hyper, loss=loss)
+    items.push(torch.cat([dRi, dRj]))
+
+
 def gather_topk(idx_local, val_local, n_users, group=None):
     """Concatenate user-sharded (idx, val) blocks in rank order (block partition => user order).
     Shards may differ by one row: blocks are padded to the largest shard for the all_gather."""

@@ -224,6 +224,19 @@ int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld, void *dst_
 int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
                     int M, int N, int K, const float *bias, float alpha, int act, void *stream);
 
+/* Row-SHARDED tables: owners gather requested rows / add returned deltas; the requester
+ * runs the BPR update (BPRMF_model.py:91-117 arithmetic) against fetched item-row copies: user rows are
+ * local and updated in place, item deltas dRi/dRj are written per triple.  If bias_col >= 0 that column
+ * of the (padded) item rows carries the item bias.  The id exchange itself is an NCCL all-to-all done by
+ * the host (elliot_b200/parallel.py::ShardedTable). */
+int eb_gather_rows_f32(const float *table, int64_t ld, const int32_t *ids, int64_t n, int width, float *out, int64_t ldo,
+                       void *stream);
+int eb_scatter_add_rows_f32(float *table, int64_t ld, const int32_t *ids, int64_t n, int width, const float *rows,
+                            int64_t ldr, void *stream);
+int eb_bpr_step_rows_f32(float *U, int64_t ldu, const int32_t *tu, const float *Ri, const float *Rj, int64_t ldr, int64_t n,
+                         int bias_col, float lr, float reg_u, float reg_b, float reg_pos, float reg_neg, float *dRi,
+                         float *dRj, double *loss, void *stream);
+
 /* Tensor-core path (tcgen05 + TMEM + TMA, bf16 mainloop, exact fp32 re-rank).  Same contract and
  * same RESULT as eb_score_topk_f32 (identical index lists and scores): the kernel keeps the 32
  * best bf16-approximate candidates per user, re-scores them exactly in fp32 and certifies the

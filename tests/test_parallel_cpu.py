@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from elliot_b200.parallel import OverlappedTableSync, ReplicatedTableSync, gather_topk, owner_of, shard_range
+from elliot_b200.parallel import (OverlappedTableSync, ReplicatedTableSync, ShardedTable, gather_topk, owner_of,
+                                  shard_range)
 
 
 def test_shard_range_partitions():
@@ -68,6 +69,22 @@ def _worker(rank, world, init_file, out_dir):
             want_W[r + step] += 1.0 + r
             want_W[7] += 0.5
     ok = ok and torch.allclose(W, want_W, atol=1e-6) and torch.allclose(osync.prev[0], want_W, atol=1e-6)
+    # row-sharded table: fetch arbitrary global rows (with duplicates), push deltas back to the owners
+    n_rows = 13
+    full = torch.arange(n_rows * 4, dtype=torch.float32).reshape(n_rows, 4)
+    lo, hi = shard_range(n_rows, rank, world)
+    st = ShardedTable(n_rows, full[lo:hi].clone(), gather_fn=lambda t, i: t[i.long()].clone(),
+                      scatter_fn=lambda t, i, r: t.index_add_(0, i.long(), r))
+    ids = torch.tensor([12, 0, 5, 5, 7, rank, 11 - rank], dtype=torch.int32)
+    got = st.fetch(ids)
+    ok = ok and torch.equal(got, full[ids.long()])
+    st.push(torch.ones(len(ids), 4) * (rank + 1))
+    dist.barrier()
+    want = full.clone()
+    for r in range(world):
+        rid = torch.tensor([12, 0, 5, 5, 7, r, 11 - r])
+        want.index_add_(0, rid, torch.ones(len(rid), 4) * (r + 1))
+    ok = ok and torch.equal(st.local, want[lo:hi])
     torch.save({"ok": ok, "V": V}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
