@@ -153,6 +153,7 @@ struct TcParams {
     float *dump;                 // optional dense n_sel x n_items approximate scores (tests)
     float eps_scale;             // c in eps_u = c * ||u|| * max||v|| + 1e-6 * (...)
     long long *prof;             // optional per-kernel cycle counters (8 values), profiling only
+    int bias_folded;             // 1: bias already inside the accumulators (extra K columns); the re-rank still adds it exactly
     int debug_mode;              // profiling only: 1 = TMEM read + max only, 2 = no compaction (results invalid)
 };
 
@@ -530,7 +531,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
                         for (int tt = 0; tt < off; tt++) ps[tt] = ps[tt] + ps[tt + off];
-                    my_v = (HAS_BIAS ? p.bias[my_i] : 0.f) + ps[0];
+                    my_v = (p.bias ? p.bias[my_i] : 0.f) + ps[0];
                 }
                 // bitonic sort over 32 lanes: (score desc, index asc)
                 float sv = my_v; int si = my_i;
@@ -549,7 +550,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 // certification: the k-th exact score must clear tau + eps_u (tau = -inf if nothing was ever dropped)
                 const float un = __shfl_sync(0xffffffffu, my_unorm, r);
-                const float eps = p.eps_scale * un * vmax_n + 1e-6f * (un * vmax_n + bmax_a);
+                const float eps = p.eps_scale * un * vmax_n + 1e-6f * un * vmax_n + 4e-5f * bmax_a;   // bias: hi+lo bf16 split, 2^-17 rel
                 const float kth = __shfl_sync(0xffffffffu, sv, p.k - 1);
                 const bool certified = !(rthresh > NEG) || (kth > rthresh + eps) || p.debug_mode != 0;
                 if (lane < p.k) {
@@ -578,8 +579,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 // ---------------------------------------------------------------- preparation kernels
 // fp32 rows [n, ld] (first d valid) -> bf16 rows [n, KP] zero padded; row norms; optional max
+// fold: 0 none; 1 (user side) columns d, d+1 = 1.0; 2 (item side) columns d, d+1 = bf16 hi / lo parts of bias[row]
 __global__ void tc_convert_kernel(const float *src, int64_t n, int d, int ld, int row0, __nv_bfloat16 *dst, int KP,
-                                  float *norms, float *norm_max) {
+                                  float *norms, float *norm_max, int fold, const float *bias) {
     const int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -590,7 +592,14 @@ __global__ void tc_convert_kernel(const float *src, int64_t n, int d, int ld, in
         for (int k = lane; k < KP; k += 32) {
             const float x = k < d ? r[k] : 0.f;
             ss += x * x;
-            dst[w * KP + k] = __float2bfloat16_rn(x);
+            __nv_bfloat16 o = __float2bfloat16_rn(x);
+            if (fold == 1 && (k == d || k == d + 1)) o = __float2bfloat16_rn(1.f);
+            if (fold == 2 && (k == d || k == d + 1)) {
+                const float b = bias[row0 + w];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+                o = k == d ? hi : __float2bfloat16_rn(b - __bfloat162float(hi));
+            }
+            dst[w * KP + k] = o;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -649,9 +658,10 @@ struct TcLayout {
     int KP;
 };
 
-static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d) {
+// fold = the item bias travels through the MMA as two extra K columns (bf16 hi + lo) against ones on the user side
+static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
     TcLayout L;
-    L.KP = (d + 63) / 64 * 64;
+    L.KP = (d + (fold ? 2 : 0) + 63) / 64 * 64;
     size_t off = 0;
     L.ubf = off; off += al((size_t)n_sel * L.KP * 2);
     L.vbf = off; off += al((size_t)n_items * L.KP * 2);
@@ -679,7 +689,7 @@ static int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const TcParams
 
 template <int KP>
 static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    const bool hb = p.bias != nullptr;
+    const bool hb = p.bias != nullptr && !p.bias_folded;    // epilogue adds the bias only when it is not folded into the MMA
     if (p.dump) return hb ? launch_tc3<KP, true, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, true, false>(a, b, p, n_mblocks, st);
     return hb ? launch_tc3<KP, false, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, false, false>(a, b, p, n_mblocks, st);
 }
@@ -690,7 +700,7 @@ using namespace eb;
 
 extern "C" size_t eb_score_topk_tc_workspace_bytes(int64_t n_sel, int32_t n_items, int d) {
     if (n_sel < 1) n_sel = 1;
-    return tc_layout(n_sel, n_items, d).total;
+    return tc_layout(n_sel, n_items, d, d + 2 <= 256).total;    // sized for the bias-folded layout (the larger one)
 }
 
 // internal entry of score_topk.cu with an output-row map (re-check of uncertified users)
@@ -714,7 +724,8 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     int cc = 0;
     if (int rc = eb_device_info(nullptr, &cc)) return rc;
     if (cc < 100) return set_err(EB_ERR_CUDA, "tcgen05 path needs compute capability 10.x (got %d)", cc);
-    const TcLayout L = tc_layout(n_sel, n_items, d);
+    const bool fold = item_bias != nullptr && d + 2 <= 256;
+    const TcLayout L = tc_layout(n_sel, n_items, d, fold);
     if (workspace_bytes < L.total) return set_err(EB_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, L.total);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
@@ -724,8 +735,8 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     EB_CUDA(cudaMemsetAsync(vstat, 0, 64, st));
     EB_CUDA(cudaMemsetAsync(flag_count, 0, 256, st));
     const int cgrid = sm_count() * 8;
-    tc_convert_kernel<<<cgrid, 256, 0, st>>>(U, n_sel, d, ld, user_begin, ubf, L.KP, unorm, nullptr);
-    tc_convert_kernel<<<cgrid, 256, 0, st>>>(V, n_items, d, ld, 0, vbf, L.KP, nullptr, vstat);
+    tc_convert_kernel<<<cgrid, 256, 0, st>>>(U, n_sel, d, ld, user_begin, ubf, L.KP, unorm, nullptr, fold ? 1 : 0, nullptr);
+    tc_convert_kernel<<<cgrid, 256, 0, st>>>(V, n_items, d, ld, 0, vbf, L.KP, nullptr, vstat, fold ? 2 : 0, item_bias);
     if (item_bias) tc_bias_kernel<<<((n_items + 31) / 32 + 255) / 256, 256, 0, st>>>(item_bias, n_items, bmax, vstat + 1);
     EB_CUDA(cudaGetLastError());
     CUtensorMap ma, mb;
@@ -735,7 +746,7 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     TcParams p{};
     p.U = U; p.V = V; p.bias = item_bias; p.d = d; p.ld = ld; p.n_items = n_items;
     p.mask_indptr = mask_indptr; p.mask_indices = mask_indices; p.user_begin = user_begin; p.n_sel = (int32_t)n_sel; p.k = k;
-    p.unorm = unorm; p.vstat = vstat; p.bmax_chunk = item_bias ? bmax : nullptr;
+    p.unorm = unorm; p.vstat = vstat; p.bmax_chunk = item_bias ? bmax : nullptr; p.bias_folded = fold ? 1 : 0;
     p.out_idx = out_idx; p.out_val = out_val; p.flag_count = flag_count; p.flag_list = flag_list; p.dump = dump;
     // bf16 RN: |x~-x| <= 2^-9|x|  =>  |u~.v~ - u.v| <= (2^-8 + 2^-18) ||u|| ||v||; +2% for fp32 accumulation and re-rank rounding
     p.eps_scale = 1.02f * (1.f / 256.f);
