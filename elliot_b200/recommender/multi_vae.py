@@ -133,6 +133,12 @@ class VariationalAutoEncoder:
             self.set_model_state(pickle.load(f))
 
 
+def epoch_user_order(num_users):
+    """One epoch's user order: `random.sample(range(users), users)` on the global `random` stream seeded with 42
+    at construction (sparse_sampler.py:10,18); pinned by tests/golden/samplers_tiny.npz."""
+    return random.sample(range(num_users), num_users)
+
+
 class MultiVAE(RecMixin, BaseRecommenderModel):
     r"""Variational Autoencoders for Collaborative Filtering (https://dl.acm.org/doi/10.1145/3178876.3186150).
     YAML keys as in the reference (multi_vae.py:42-52)."""
@@ -172,7 +178,7 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
         self._update_count = 0
         for it in self.iterate(self._epochs):
             loss = 0
-            order = random.sample(range(self._num_users), self._num_users)      # sparse_sampler.py:18
+            order = epoch_user_order(self._num_users)
             order = torch.tensor(order, dtype=torch.int32, device=self._device)
             for s in range(0, self._num_users, self._batch_size):
                 rows = order[s:s + self._batch_size].contiguous()

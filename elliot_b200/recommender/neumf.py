@@ -14,12 +14,46 @@ TensorFlow parity is UNPINNED (oracle/tf_models.py::neumf_forward_backward is th
 """
 import math
 import pickle
+import random
 
 import numpy as np
 import torch
 
 from .. import ops
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
+
+
+class ReferenceSampler:
+    """Host replay of the reference's pointwise sampler (neural/NeuMF/custom_sampler.py:14-48): legacy
+    np.random.seed(42) + random.seed(42); per epoch the SET of positives (u, i, 1), for each positive (in the
+    set's iteration order) m negatives drawn with np.random.randint and redrawn while they hit a train item,
+    collected in a SET (duplicates collapse), then `random.sample` shuffles positives + negatives.  The order
+    depends on CPython's set iteration order for int tuples, so it has to run in Python like the reference;
+    pinned by tests/golden/samplers_tiny.npz.  `b200_sampler: reference` selects it (small data only)."""
+
+    def __init__(self, i_train_dict, m):
+        np.random.seed(42)
+        random.seed(42)
+        self._rows = {u: list(set(i_train_dict[u])) for u in i_train_dict}
+        self._n_items = len({k for a in i_train_dict.values() for k in a.keys()})
+        self._m = m
+
+    def epoch(self):
+        draw, n_items = np.random.randint, self._n_items
+        positives = {(u, i, 1) for u, items in self._rows.items() for i in items}
+        negatives = set()
+        for u, _, _ in positives:
+            mine = self._rows[u]
+            for _ in range(self._m):
+                j = draw(n_items)
+                while j in mine:
+                    j = draw(n_items)
+                negatives.add((u, j, 0))
+        samples = list(positives)
+        samples.extend(list(negatives))
+        samples = random.sample(samples, len(samples))
+        arr = np.array(samples, dtype=np.int64).reshape(-1, 3)
+        return arr[:, 0], arr[:, 1], arr[:, 2]
 
 
 class NeuralMatrixFactorizationModel:
@@ -148,6 +182,10 @@ class NeuMF(RecMixin, BaseRecommenderModel):
                                                      self._seed, self._device)
         self._gen = torch.Generator(device=self._device); self._gen.manual_seed(42)
         self._epoch = 0
+        self._sampler_kind = getattr(self._params, "b200_sampler", "device")
+        if self._sampler_kind not in ("device", "reference"):
+            raise Exception("b200_sampler must be 'device' or 'reference'")
+        self._ref_sampler = ReferenceSampler(self._data.i_train_dict, self._m) if self._sampler_kind == "reference" else None
 
     @property
     def name(self):
@@ -158,11 +196,16 @@ class NeuMF(RecMixin, BaseRecommenderModel):
             return self.restore_weights()
         for it in self.iterate(self._epochs):
             loss, steps = 0.0, 0
-            u, i, y = ops.neumf_sample(self._num_users, self._num_items, self._indptr, self._sorted_idx, self._m,
-                                       42 + 1000003 * self._epoch)
+            if self._ref_sampler is not None:                   # exact replay of the reference's epoch sample list
+                hu, hi, hy = self._ref_sampler.epoch()
+                u = torch.from_numpy(hu.astype(np.int32)).to(self._device); i = torch.from_numpy(hi.astype(np.int32)).to(self._device)
+                y = torch.from_numpy(hy.astype(np.float32)).to(self._device)
+            else:
+                u, i, y = ops.neumf_sample(self._num_users, self._num_items, self._indptr, self._sorted_idx, self._m,
+                                           42 + 1000003 * self._epoch)
+                perm = torch.randperm(u.numel(), device=self._device, generator=self._gen)        # random.sample shuffle (:44)
+                u, i, y = u[perm].contiguous(), i[perm].contiguous(), y[perm].contiguous()
             self._epoch += 1
-            perm = torch.randperm(u.numel(), device=self._device, generator=self._gen)            # random.sample shuffle (:44)
-            u, i, y = u[perm].contiguous(), i[perm].contiguous(), y[perm].contiguous()
             for s in range(0, u.numel(), self._batch_size):
                 e = min(s + self._batch_size, u.numel())
                 loss += float(self._model.train_step((u[s:e], i[s:e], y[s:e])).item()); steps += 1

@@ -162,7 +162,50 @@ def make_split_case():
     print("split", len(df), len(train), len(test))
 
 
+def make_sampler_cases():
+    """Reference NeuMF pointwise sampler (neural/NeuMF/custom_sampler.py:14-48) and the autoencoder row sampler
+    (dataset/samplers/sparse_sampler.py:9-25) on the tiny case: pins epoch sample order / user-batch order."""
+    import scipy.sparse as sp
+    ns = _load("ref_neumf_sampler", "elliot/recommender/neural/NeuMF/custom_sampler.py")
+    ss = _load("ref_sparse_sampler", "elliot/dataset/samplers/sparse_sampler.py")
+    g = np.load(os.path.join(OUT, "bprmf_tiny.npz"))
+    nu = len(g["users"])
+    i_train = {u: {int(i): 1.0 for i in g["ui_indices"][g["ui_indptr"][u]:g["ui_indptr"][u + 1]]} for u in range(nu)}
+    out = {}
+    for m in (0, 3):
+        smp = ns.Sampler(i_train, m)
+        eps = []
+        for ep in range(2):
+            u, i, b = [], [], []
+            for bu, bi, bb in smp.step(64):
+                u.extend(bu.tolist()); i.extend(bi.tolist()); b.extend(bb.tolist())
+            eps.append(np.array([u, i, b], dtype=np.int64))
+        out[f"neumf_m{m}_ep0"], out[f"neumf_m{m}_ep1"] = eps
+    rows = [u for u in range(nu) for _ in i_train[u]]; cols = [i for u in range(nu) for i in i_train[u]]
+    mat = sp.csr_matrix((np.ones(len(rows), dtype=np.float32), (rows, cols)), shape=(nu, len(g["items"])))
+    vs = ss.Sampler(mat)
+    order = []
+    for ep in range(2):
+        ep_rows = []
+        for batch in vs.step(nu, 16):
+            # recover the user of each dense row from its item pattern (rows are unique in this case)
+            ep_rows.append(batch.shape[0])
+        order.append(ep_rows)
+    import random
+    random.seed(42)
+    perm = [random.sample(range(nu), nu) for _ in range(2)]            # what sparse_sampler.py:18 draws, epoch by epoch
+    # cross-check against the reference's dense batches
+    vs2 = ss.Sampler(mat)
+    for ep in range(2):
+        got = np.concatenate([b for b in vs2.step(nu, 16)])
+        assert np.array_equal(got, mat[perm[ep]].toarray())
+    out["vae_perm"] = np.array(perm, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "samplers_tiny.npz"), **out)
+    print("samplers", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     make_split_case()
     make_case("tiny", n_users=60, n_items=48, mean_pos=8, d=10, seed_data=1, model_seed=42, epochs=2, k=10)
+    make_sampler_cases()
     make_case("small", n_users=400, n_items=300, mean_pos=20, d=64, seed_data=2, model_seed=7, epochs=2, k=10)

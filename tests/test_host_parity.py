@@ -97,3 +97,27 @@ def test_base_model_contract_errors():
         M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(validation_rate=5), epochs=2))
     m = M(data, SimpleNamespace(), SimpleNamespace(meta=SimpleNamespace(), epochs=3, seed=7))
     assert m.get_base_params_shortcut() == "seed=7_e=3_bs=-1"
+
+
+def test_neumf_reference_sampler_replays_reference_epochs():
+    """custom_sampler.py:14-48 (NeuMF): same (user, item, label) sequence for two epochs, m = 0 and m = 3."""
+    from elliot_b200.recommender.neumf import ReferenceSampler
+    g = np.load(os.path.join(GOLDEN, "bprmf_tiny.npz")); s = np.load(os.path.join(GOLDEN, "samplers_tiny.npz"))
+    nu = len(g["users"])
+    i_train = {u: {int(i): 1.0 for i in g["ui_indices"][g["ui_indptr"][u]:g["ui_indptr"][u + 1]]} for u in range(nu)}
+    for m in (0, 3):
+        smp = ReferenceSampler(i_train, m)
+        for ep in range(2):
+            u, i, y = smp.epoch()
+            want = s[f"neumf_m{m}_ep{ep}"]
+            assert np.array_equal(u, want[0]) and np.array_equal(i, want[1]) and np.array_equal(y, want[2]), (m, ep)
+
+
+def test_multivae_epoch_order_replays_reference():
+    """sparse_sampler.py:9-25: per-epoch user permutation from random.seed(42)."""
+    import random
+    from elliot_b200.recommender.multi_vae import epoch_user_order
+    s = np.load(os.path.join(GOLDEN, "samplers_tiny.npz"))
+    random.seed(42)
+    for ep in range(2):
+        assert epoch_user_order(s["vae_perm"].shape[1]) == s["vae_perm"][ep].tolist()
