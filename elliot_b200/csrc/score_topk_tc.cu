@@ -32,7 +32,7 @@ namespace eb {
 
 constexpr int TC_BM = 128;        // users per block (UMMA M)
 constexpr int TC_KC = 32;         // candidates kept per user (one per lane in the re-rank)
-constexpr int TC_THREADS = 192;   // 6 warps
+
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
