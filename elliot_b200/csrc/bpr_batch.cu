@@ -179,11 +179,11 @@ __global__ void __launch_bounds__(256) delta_kernel(const float4 *__restrict__ c
     }
 }
 __global__ void __launch_bounds__(256) apply_delta_kernel(float4 *__restrict__ cur, float4 *__restrict__ prev,
-                                                          const float4 *__restrict__ sum, int64_t n4) {
+                                                          const float4 *__restrict__ sum, int64_t n4, float scale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 b = prev[i], s = sum[i];
-        const float4 r = make_float4(b.x + s.x, b.y + s.y, b.z + s.z, b.w + s.w);
+        const float4 r = make_float4(b.x + scale * s.x, b.y + scale * s.y, b.z + scale * s.z, b.w + scale * s.w);
         cur[i] = r; prev[i] = r;
     }
 }
@@ -223,11 +223,11 @@ extern "C" int eb_table_delta_f32(const float *cur, const float *prev, float *de
     return EB_OK;
 }
 
-extern "C" int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, void *stream) {
+extern "C" int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, float scale, void *stream) {
     EB_ARG(cur && prev && delta_sum && n >= 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
     if (n == 0) return EB_OK;
     int64_t grid = (n / 4 + 255) / 256; const int64_t cap = (int64_t)eb::sm_count() * 8; if (grid > cap) grid = cap;
-    eb::apply_delta_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((float4 *)cur, (float4 *)prev, (const float4 *)delta_sum, n / 4);
+    eb::apply_delta_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((float4 *)cur, (float4 *)prev, (const float4 *)delta_sum, n / 4, scale);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

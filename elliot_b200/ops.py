@@ -233,10 +233,10 @@ def table_delta_f32(cur, prev, delta):
         check(lib().eb_table_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta), cur.numel(), _stream(cur)))
 
 
-def table_apply_delta_f32(cur, prev, delta_sum):
+def table_apply_delta_f32(cur, prev, delta_sum, scale=1.0):
     _need_cuda(cur, prev, delta_sum)
     with torch.cuda.device(cur.device):
-        check(lib().eb_table_apply_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), cur.numel(), _stream(cur)))
+        check(lib().eb_table_apply_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), cur.numel(), scale, _stream(cur)))
 
 
 def to_bf16(src, transpose=False, out=None):

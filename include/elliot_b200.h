@@ -203,9 +203,10 @@ int eb_neumf_pair_head(const float *Umf, const float *Imf, int64_t ldt, int f, i
 
 /* Multi-GPU reconciliation of a REPLICATED table (item factors / biases): every
  * rank computes delta = cur - prev, the host all-reduces `delta` (NCCL), then
- * cur = prev = prev + sum(delta).  No reference counterpart (the reference is single-device). */
+ * cur = prev = prev + scale * sum(delta)  (scale 1 = every rank's updates applied in full, 1/world = averaged,
+ * the stable default when many ranks hit the same rows).  No reference counterpart (single-device reference). */
 int eb_table_delta_f32(const float *cur, const float *prev, float *delta, int64_t n, void *stream);
-int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, void *stream);
+int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, float scale, void *stream);
 /* overlapped variant (the all-reduce of step k runs while step k+1 computes):
  *   cur += delta_sum - delta_local;  prev += delta_sum */
 int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_sum, const float *delta_local, int64_t n,

@@ -33,7 +33,7 @@ def _worker(rank, world, init_file, out_dir):
     V = torch.randn(16, 8); b = torch.randn(16)
     V0, b0 = V.clone(), b.clone()
     sync = ReplicatedTableSync([V, b], delta_fn=lambda c, p, d: d.copy_(c - p),
-                               apply_fn=lambda c, p, s: (p.add_(s), c.copy_(p)))
+                               apply_fn=lambda c, p, s, k: (p.add_(s * k), c.copy_(p)), reduce="sum")
     for step in range(3):
         # each rank touches different rows with different amounts (its local Hogwild step)
         V[rank * 4 + step] += (rank + 1) * 0.5
@@ -54,6 +54,15 @@ def _worker(rank, world, init_file, out_dir):
     val = idx.float() * 0.5
     gi, gv = gather_topk(idx, val, n_users)
     ok = ok and torch.equal(gi[:, 0], torch.arange(n_users, dtype=torch.int32)) and torch.equal(gv, gi.float() * 0.5)
+    # averaged reduction through one flat buffer: replicas agree and hold the mean of the rank updates
+    flat = torch.zeros(12)
+    A, Bv = flat[:8].view(2, 4), flat[8:]
+    msync = ReplicatedTableSync([A, Bv], delta_fn=lambda c, p, d: d.copy_(c - p),
+                                apply_fn=lambda c, p, s, k: (p.add_(s * k), c.copy_(p)), reduce="mean", flat=flat)
+    A += float(rank + 1); Bv -= 2.0 * rank
+    msync.sync()
+    ok = ok and torch.allclose(A, torch.full((2, 4), sum(r + 1 for r in range(world)) / world)) \
+        and torch.allclose(Bv, torch.full((4,), -2.0 * sum(range(world)) / world))
     # overlapped (one-step-late) variant: after flush() the replicas agree and nothing is lost or doubled
     W = torch.zeros(8, 4)
     osync = OverlappedTableSync([W], delta_fn=lambda c, p, d: d.copy_(c - p),
