@@ -209,11 +209,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync", default="overlap", choices=["overlap", "simple"],
+                    help="N>1: item-table reconciliation one step late on a side stream (overlap) or in-line (simple)")
+    ap.add_argument("--reserve-sms", type=int, default=16,
+                    help="N>1 with --sync overlap: SMs the persistent training grid leaves free for the NCCL kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+    if args.sync == "overlap":
+        os.environ.setdefault("NCCL_MAX_CTAS", str(max(args.reserve_sms, 1)))   # the collective fits the reserved SMs
     import torch
     import torch.distributed as dist
     from elliot_b200 import ops
@@ -241,8 +247,16 @@ def main():
     counter = [0]
     item_sync = None
     if world > 1:
-        from elliot_b200.parallel import ReplicatedTableSync
-        item_sync = ReplicatedTableSync([V, b], reduce="mean", flat=items_flat)
+        from elliot_b200.parallel import ReplicatedTableSync, OverlappedTableSync
+        if args.sync == "overlap":
+            item_sync = OverlappedTableSync([V, b], reduce="mean", flat=items_flat)
+        else:
+            item_sync = ReplicatedTableSync([V, b], reduce="mean", flat=items_flat)
+    reserve = args.reserve_sms if (world > 1 and args.sync == "overlap") else 0
+
+    def flush_items():
+        if world > 1 and args.sync == "overlap":
+            item_sync.flush()
 
     def sync_items():
         # the path's one exchange step: all ranks add up their item-row deltas (NCCL all-reduce)
@@ -250,13 +264,14 @@ def main():
 
     def step():
         ops.bpr_step_sampled_f32(U, V, b, D, N_USERS, N_ITEMS, indptr, indices, BATCH, seed, counter[0] * BATCH, *HP,
-                                 loss=loss)
+                                 loss=loss, reserve_sms=reserve)
         counter[0] += 1
 
     for _ in range(W):
         step()
         if world > 1:
             sync_items()
+    flush_items()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -271,6 +286,7 @@ def main():
         ks[k].record(); step(); ke[k].record()
         if world > 1:
             sync_items()
+    flush_items()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -304,11 +320,13 @@ def main():
             if k >= 2:
                 total += loss_host[sl].item()
             with torch.cuda.stream(streams[sl]):
-                ops.bpr_step_host_f32(U, V, b, D, *host[k % pool], *HP, staging[sl], loss_dev2[sl], loss_host[sl], sync=False)
+                ops.bpr_step_host_f32(U, V, b, D, *host[k % pool], *HP, staging[sl], loss_dev2[sl], loss_host[sl], sync=False,
+                                      reserve_sms=reserve)
                 if world > 1:
                     sync_items()
         for st_ in streams:
             st_.synchronize()
+        flush_items()
         return total
     torch.cuda.synchronize()
     e2e_steps(3)
@@ -385,6 +403,8 @@ def main():
                    "global_batch": BATCH * world,
                    "parallelism": "user rows sharded per GPU; item table + biases replicated, reconciled every step by ONE "
                                   "NCCL all-reduce of the per-rank deltas (averaged: local-SGD style, stable at any N)"
+                                  + (f"; all-reduce of step k runs on a side stream beside step k+1 (applied one step late), "
+                                     f"training grid leaves {reserve} SMs free for it" if reserve else "; in-line")
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: 256 MB user table + 400 MB CSR per GPU vs 126 MB L2, "
                          "fresh random rows every step (no L2 flush needed)"},
@@ -395,7 +415,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": 12 * BATCH, "d2h_bytes_per_step": 8,
                 "path": "eb_bpr_step_host_f32: pinned host int32 triples -> H2D -> kernel -> D2H loss every step; "
                         "two streams so step k+1 copies while step k computes; wall-clock timed"},
-        "gpu_launches": K, "clocks": clk, "finite": finite, "loss_sum": loss.item(),
+        "gpu_launches": K * (1 if world == 1 else 3), "clocks": clk, "finite": finite, "loss_sum": loss.item(),
         "scoring": {"metric": "scored_users_per_sec", "value": S_USERS * world / (score_ms * 1e-3), "unit": "users/s",
                     "config": {"workload": f"{S_USERS} users/GPU x {N_ITEMS} items, d={D}, k=10, item bias + train mask "
                                            "(~100 items/user), tcgen05 bf16 mainloop + exact fp32 re-rank",

@@ -188,28 +188,31 @@ __global__ void __launch_bounds__(256) apply_delta_kernel(float4 *__restrict__ c
     }
 }
 // overlapped variant: cur already contains newer local updates; add what the OTHER ranks contributed
-//   cur += (sum - local);  prev += sum
-__global__ void __launch_bounds__(256) apply_delta_late_kernel(float4 *__restrict__ cur, float4 *__restrict__ prev,
+//   cur += (scale*sum - local);  prev += scale*sum
+// cur is updated with vector atomics: a training kernel on another stream may be adding to the same rows.
+__global__ void __launch_bounds__(256) apply_delta_late_kernel(float *__restrict__ cur, float4 *__restrict__ prev,
                                                                const float4 *__restrict__ sum, const float4 *__restrict__ local,
-                                                               int64_t n4) {
+                                                               int64_t n4, float scale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 s = sum[i], l = local[i];
-        float4 c = cur[i], b = prev[i];
-        c.x += s.x - l.x; c.y += s.y - l.y; c.z += s.z - l.z; c.w += s.w - l.w;
+        float4 s = sum[i];
+        const float4 l = local[i];
+        s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+        float4 b = prev[i];
+        red_add_v4(cur + 4 * i, make_float4(s.x - l.x, s.y - l.y, s.z - l.z, s.w - l.w));
         b.x += s.x; b.y += s.y; b.z += s.z; b.w += s.w;
-        cur[i] = c; prev[i] = b;
+        prev[i] = b;
     }
 }
 }  // namespace eb
 
 extern "C" int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_sum, const float *delta_local, int64_t n,
-                                             void *stream) {
+                                             float scale, void *stream) {
     EB_ARG(cur && prev && delta_sum && delta_local && n >= 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");
     if (n == 0) return EB_OK;
     int64_t grid = (n / 4 + 255) / 256; const int64_t cap = (int64_t)eb::sm_count() * 8; if (grid > cap) grid = cap;
-    eb::apply_delta_late_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((float4 *)cur, (float4 *)prev, (const float4 *)delta_sum,
-                                                                                  (const float4 *)delta_local, n / 4);
+    eb::apply_delta_late_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(cur, (float4 *)prev, (const float4 *)delta_sum,
+                                                                                  (const float4 *)delta_local, n / 4, scale);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

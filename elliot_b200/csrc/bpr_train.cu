@@ -35,14 +35,6 @@ struct HogwildParams {
     int32_t *out_u, *out_i, *out_j;
 };
 
-__device__ __forceinline__ void red_add_v4(float *p, float4 v) {
-    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void red_add_f32(float *p, float v) {
-    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
 
 // u uniform over users, i uniform over the user's train items, j uniform over the
 // complement (rejection against the sorted CSR row) — custom_sampler.py:31-42 semantics,
@@ -210,13 +202,15 @@ __global__ void __launch_bounds__(256) philox_sample_kernel(const HogwildParams 
 }
 
 template <int DP, bool SAMPLE, bool ATOMIC>
-static int launch_hogwild_t(const HogwildParams &p, cudaStream_t st) {
+static int launch_hogwild_t(const HogwildParams &p, int reserve_sms, cudaStream_t st) {
     int per_sm = 0;
     EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bpr_hogwild_kernel<DP, SAMPLE, ATOMIC>, 256, 0));
     if (per_sm < 1) per_sm = 1;
     int64_t tiles = (p.n + 31) / 32;
     int64_t want = (tiles + 7) / 8;
-    int64_t grid = (int64_t)sm_count() * per_sm;
+    int sms = sm_count() - reserve_sms;  // SMs left free for a concurrent collective (NCCL) kernel
+    if (sms < 1) sms = 1;
+    int64_t grid = (int64_t)sms * per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     bpr_hogwild_kernel<DP, SAMPLE, ATOMIC><<<(unsigned)grid, 256, 0, st>>>(p);
@@ -225,10 +219,13 @@ static int launch_hogwild_t(const HogwildParams &p, cudaStream_t st) {
 }
 
 template <bool SAMPLE>
-static int launch_hogwild(const HogwildParams &p, int dp, bool atomic, cudaStream_t st) {
+static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
+    const bool atomic = !(flags & 1);
+    const int reserve = (flags >> 8) & 0xff;
 #define EB_CASE(DPV)                                                                           \
     case DPV:                                                                                  \
-        return atomic ? launch_hogwild_t<DPV, SAMPLE, true>(p, st) : launch_hogwild_t<DPV, SAMPLE, false>(p, st);
+        return atomic ? launch_hogwild_t<DPV, SAMPLE, true>(p, reserve, st)                           \
+                      : launch_hogwild_t<DPV, SAMPLE, false>(p, reserve, st);
     switch (dp) {
         EB_CASE(8) EB_CASE(16) EB_CASE(32) EB_CASE(64) EB_CASE(128) EB_CASE(256)
         default: return set_err(EB_ERR_ARG, "row stride ld=%d must be one of 8,16,32,64,128,256 floats", dp);
@@ -409,7 +406,7 @@ extern "C" int eb_bpr_step_f32(float *U, float *V, float *item_bias, int d, int 
     HogwildParams p{};
     p.U = U; p.V = V; p.b = item_bias; p.ld = ld; p.tu = tu; p.ti = ti; p.tj = tj; p.n = n;
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
-    return launch_hogwild<false>(p, ld, !(flags & 1), (cudaStream_t)stream);
+    return launch_hogwild<false>(p, ld, flags, (cudaStream_t)stream);
 }
 
 extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int d, int ld, int32_t n_users,
@@ -427,7 +424,7 @@ extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
-    return launch_hogwild<true>(p, ld, !(flags & 1), (cudaStream_t)stream);
+    return launch_hogwild<true>(p, ld, flags, (cudaStream_t)stream);
 }
 
 extern "C" int eb_bpr_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,

@@ -71,4 +71,13 @@ __device__ static inline bool contains_sorted(const int32_t *__restrict__ a, int
     return lo < len && __ldg(a + lo) == key;
 }
 
+// 128-bit / 32-bit fire-and-forget float adds (REDG.E.ADD.F32x4 / REDG.E.ADD.F32 on sm_100a)
+__device__ __forceinline__ void red_add_v4(float *p, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 }  // namespace eb

@@ -57,7 +57,7 @@ def bpr_step_f32(U, V, b, d, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, los
 
 
 def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u, reg_b, reg_pos,
-                         reg_neg, loss=None, out=None, racy=False):
+                         reg_neg, loss=None, out=None, racy=False, reserve_sms=0):
     """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream)."""
     _need_cuda(U, V, b, indptr, indices, loss)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
@@ -68,7 +68,8 @@ def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed,
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_sampled_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), n_users, n_items, _ptr(indptr),
                                             _ptr(indices), n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg,
-                                            _ptr(loss), _ptr(ou), _ptr(oi), _ptr(oj), 1 if racy else 0, _stream(U)))
+                                            _ptr(loss), _ptr(ou), _ptr(oi), _ptr(oj),
+                                            (1 if racy else 0) | ((int(reserve_sms) & 0xff) << 8), _stream(U)))
 
 
 def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0):
@@ -82,7 +83,7 @@ def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0):
 
 
 def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, reg_pos, reg_neg, staging, loss_dev,
-                      loss_host, racy=False, sync=True):
+                      loss_host, racy=False, sync=True, reserve_sms=0):
     """End-to-end step from HOST (pinned) int32 triples; returns after the loss is back on the host."""
     _need_cuda(U, V, b, staging, loss_dev)
     n = tu_host.numel()
@@ -90,7 +91,8 @@ def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, r
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_host_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), _ptr(tu_host), _ptr(ti_host),
                                          _ptr(tj_host), n, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(staging),
-                                         _ptr(loss_dev), _ptr(loss_host), (1 if racy else 0) | (0 if sync else 2), _stream(U)))
+                                         _ptr(loss_dev), _ptr(loss_host), (1 if racy else 0) | (0 if sync else 2) | ((int(reserve_sms) & 0xff) << 8),
+                                         _stream(U)))
 
 
 class _Workspace:
@@ -383,11 +385,11 @@ def neumf_pair_head(Umf, Imf, f, u0, n_ub, n_items, h3, wp, bp, prob):
           _ptr(bp), _ptr(prob), prob.stride(0))
 
 
-def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local):
+def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local, scale=1.0):
     _need_cuda(cur, prev, delta_sum, delta_local)
     with torch.cuda.device(cur.device):
         check(lib().eb_table_apply_delta_late_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), _ptr(delta_local), cur.numel(),
-                                                  _stream(cur)))
+                                                  float(scale), _stream(cur)))
 
 
 # ---------------------------------------------------------------- row-sharded tables (sharded.cu)

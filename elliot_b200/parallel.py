@@ -61,18 +61,22 @@ class OverlappedTableSync:
     (Hogwild tolerates the extra staleness; nothing is lost or double counted):
 
         after step k  :  local_k = T - T_prev        (compute stream);  all_reduce(copy of local_k) on the comm stream
-        after step k+1:  wait for that all-reduce;  T += sum_k - local_k;  T_prev += sum_k;  then start round k+1
+        after step k+1:  wait for that all-reduce;  T += scale*sum_k - local_k;  T_prev += scale*sum_k;  start round k+1
 
-    delta_fn / late_fn default to the CUDA kernels; CPU tests inject torch equivalents.
+    The collective only overlaps if the compute kernel leaves SMs free for it: launch the persistent training
+    grid with `reserve_sms` (flags bits 8..15 of eb_bpr_step_sampled_f32) >= the collective's CTA count.
+    reduce / flat: as in ReplicatedTableSync.  delta_fn / late_fn default to the CUDA kernels; CPU tests inject
+    torch equivalents.
     """
 
-    def __init__(self, tables, group=None, delta_fn=None, late_fn=None, stream=None):
+    def __init__(self, tables, group=None, delta_fn=None, late_fn=None, stream=None, reduce="mean", flat=None):
         from . import ops
-        self.tables = list(tables)
+        assert reduce in ("mean", "sum")
+        self.tables = [flat] if flat is not None else list(tables)
         self.prev = [t.clone() for t in self.tables]
         self.local = [torch.zeros_like(t) for t in self.tables]
         self.sum = [torch.zeros_like(t) for t in self.tables]
-        self.group = group
+        self.group, self.reduce = group, reduce
         self._delta = delta_fn or ops.table_delta_f32
         self._late = late_fn or ops.table_apply_delta_late_f32
         self.cuda = self.tables[0].is_cuda
@@ -81,13 +85,17 @@ class OverlappedTableSync:
         self.ready = torch.cuda.Event() if self.cuda else None
         self.done = torch.cuda.Event() if self.cuda else None
 
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
     def _finish(self):
         if not self.pending:
             return
         if self.cuda:
             torch.cuda.current_stream(self.tables[0].device).wait_event(self.done)
+        scale = 1.0 / self._world() if self.reduce == "mean" else 1.0
         for t, p, s, l in zip(self.tables, self.prev, self.sum, self.local):
-            self._late(t, p, s, l)
+            self._late(t, p, s, l, scale)
         self.pending = False
 
     def sync(self):
@@ -96,7 +104,7 @@ class OverlappedTableSync:
         for t, p, l, s in zip(self.tables, self.prev, self.local, self.sum):
             self._delta(t, p, l)
             s.copy_(l)
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        world = self._world()
         if self.cuda:
             self.ready.record()
             with torch.cuda.stream(self.comm):

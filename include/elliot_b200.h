@@ -55,7 +55,8 @@ int eb_device_info(int *sm_count, int *cc);
 /* Throughput mode: fp32, one launch over n materialised triples, rows updated
  * with 128-bit vector atomics (Hogwild: reads within a launch may be stale).
  * loss (optional, device double[1]) += sum softplus(-(x_ui-x_uj)).
- * flags: bit0 = plain stores instead of atomics (racy Hogwild). */
+ * flags: bit0 = plain stores instead of atomics (racy Hogwild); bits 8..15 = number of SMs
+ * the persistent grid leaves free (so a collective kernel on another stream can run beside it). */
 int eb_bpr_step_f32(float *U, float *V, float *item_bias, int d, int ld,
                     const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
                     float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
@@ -208,9 +209,9 @@ int eb_neumf_pair_head(const float *Umf, const float *Imf, int64_t ldt, int f, i
 int eb_table_delta_f32(const float *cur, const float *prev, float *delta, int64_t n, void *stream);
 int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, int64_t n, float scale, void *stream);
 /* overlapped variant (the all-reduce of step k runs while step k+1 computes):
- *   cur += delta_sum - delta_local;  prev += delta_sum */
+ *   cur += scale*delta_sum - delta_local;  prev += scale*delta_sum */
 int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_sum, const float *delta_local, int64_t n,
-                                  void *stream);
+                                  float scale, void *stream);
 
 /* ------------------------------------------------------------------------
  * Dense layers (MultiVAE encoder/decoder, NeuMF MLP): bf16 tensor-core GEMM

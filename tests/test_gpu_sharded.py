@@ -55,3 +55,52 @@ def test_sharded_step_equals_sequential_on_conflict_free_batch(golden_small, d, 
         assert np.abs(Vd.cpu().numpy()[:, d] - b).max() < 2e-6
         assert not Ud[:, d:].any()                                # the bias column never leaks into the user rows
     assert loss.item() > 0
+
+
+def test_table_delta_apply_and_late_kernels():
+    """Replicated-table reconciliation kernels: delta = cur - prev; apply: cur = prev = prev + scale*sum;
+    late: cur += scale*sum - local, prev += scale*sum (atomic on cur)."""
+    g = torch.Generator(device=DEV); g.manual_seed(3)
+    n = 4 * 1031
+    prev = torch.randn(n, device=DEV, generator=g); cur = prev + torch.randn(n, device=DEV, generator=g) * 0.1
+    d = torch.empty_like(cur)
+    ops.table_delta_f32(cur, prev, d)
+    assert torch.equal(d, cur - prev)
+    other = torch.randn(n, device=DEV, generator=g) * 0.1          # stands in for the other ranks' deltas
+    s = d + other
+    c1, p1 = cur.clone(), prev.clone()
+    ops.table_apply_delta_f32(c1, p1, s, 0.5)
+    want = prev + 0.5 * s
+    assert torch.allclose(c1, want, atol=1e-6) and torch.equal(c1, p1)
+    c2, p2 = cur.clone(), prev.clone()
+    newer = torch.randn(n, device=DEV, generator=g) * 0.01          # local updates made while the all-reduce ran
+    c2 += newer
+    ops.table_apply_delta_late_f32(c2, p2, s, d, 0.5)
+    assert torch.allclose(p2, want, atol=1e-6)
+    assert torch.allclose(c2, want + newer, atol=1e-6)
+
+
+def test_reserved_sms_grid_gives_same_statistics(golden_small):
+    """flags bits 8..15 only shrink the persistent grid: the sampled triples (a pure function of the counter) are
+    identical and the update is the same Hogwild step."""
+    g = golden_small
+    nu, ni = len(g["users"]), len(g["items"])
+    ip = g["ui_indptr"].astype(np.int64); srt = g["ui_indices"].astype(np.int32).copy()
+    for x in range(nu):
+        srt[ip[x]:ip[x + 1]].sort()
+    indptr = torch.from_numpy(ip).to(DEV); indices = torch.from_numpy(srt).to(DEV)
+    n = 4096
+    outs = []
+    for reserve in (0, 100):
+        gen = torch.Generator(device=DEV); gen.manual_seed(1)
+        U = torch.randn(nu, 16, device=DEV, generator=gen) * 0.1; V = torch.randn(ni, 16, device=DEV, generator=gen) * 0.1
+        b = torch.zeros(ni, device=DEV)
+        out = tuple(torch.empty(n, dtype=torch.int32, device=DEV) for _ in range(3))
+        loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+        ops.bpr_step_sampled_f32(U, V, b, 16, nu, ni, indptr, indices, n, 5, 0, 0.05, 0.0025, 0.0, 0.0025, 0.00025,
+                                 loss=loss, out=out, reserve_sms=reserve)
+        outs.append((out, loss.item(), U.clone(), V.clone()))
+    for a, c in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, c)
+    assert abs(outs[0][1] - outs[1][1]) < 1e-3 * abs(outs[0][1])
+    assert torch.allclose(outs[0][2], outs[1][2], atol=1e-3) and torch.allclose(outs[0][3], outs[1][3], atol=1e-3)

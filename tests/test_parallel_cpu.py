@@ -66,7 +66,7 @@ def _worker(rank, world, init_file, out_dir):
     # overlapped (one-step-late) variant: after flush() the replicas agree and nothing is lost or doubled
     W = torch.zeros(8, 4)
     osync = OverlappedTableSync([W], delta_fn=lambda c, p, d: d.copy_(c - p),
-                                late_fn=lambda c, p, s, l: (c.add_(s - l), p.add_(s)))
+                                late_fn=lambda c, p, s, l, k: (c.add_(s * k - l), p.add_(s * k)), reduce="sum")
     for step in range(4):
         W[rank + step] += 1.0 + rank
         W[7] += 0.5
@@ -78,6 +78,18 @@ def _worker(rank, world, init_file, out_dir):
             want_W[r + step] += 1.0 + r
             want_W[7] += 0.5
     ok = ok and torch.allclose(W, want_W, atol=1e-6) and torch.allclose(osync.prev[0], want_W, atol=1e-6)
+    # overlapped + averaged + flat: replicas end identical and equal the running mean of the rank updates
+    oflat = torch.zeros(12)
+    OA, Ob = oflat[:8].view(2, 4), oflat[8:]
+    omsync = OverlappedTableSync([OA, Ob], delta_fn=lambda c, p, d: d.copy_(c - p),
+                                 late_fn=lambda c, p, s, l, k: (c.add_(s * k - l), p.add_(s * k)), reduce="mean", flat=oflat)
+    for step in range(3):
+        OA += float(rank + 1); Ob -= 2.0 * rank
+        omsync.sync()
+    omsync.flush()
+    ok = ok and torch.allclose(OA, torch.full((2, 4), 3.0 * sum(r + 1 for r in range(world)) / world), atol=1e-6) \
+        and torch.allclose(Ob, torch.full((4,), -6.0 * sum(range(world)) / world), atol=1e-6) \
+        and torch.allclose(omsync.prev[0], oflat, atol=1e-6)
     # row-sharded table: fetch arbitrary global rows (with duplicates), push deltas back to the owners
     n_rows = 13
     full = torch.arange(n_rows * 4, dtype=torch.float32).reshape(n_rows, 4)
