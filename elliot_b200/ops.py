@@ -392,6 +392,16 @@ def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local, scale=1.0):
                                                   float(scale), _stream(cur)))
 
 
+def partition_streams(device, reserve_sms, n_streams=1):
+    """Streams bound to a green context that leaves >= reserve_sms SMs of `device` free (partition.cu).
+    Returns (list of torch streams, SMs in the partition)."""
+    arr = (ctypes.c_void_p * n_streams)()
+    granted = ctypes.c_int(0)
+    with torch.cuda.device(device):
+        check(lib().eb_partition_streams_create(int(reserve_sms), n_streams, arr, ctypes.byref(granted)))
+    return [torch.cuda.ExternalStream(int(arr[k]), device=device) for k in range(n_streams)], granted.value
+
+
 # ---------------------------------------------------------------- row-sharded tables (sharded.cu)
 def gather_rows_f32(table, ids, width=None, out=None):
     _need_cuda(table, ids, out); _chk_idx(ids)

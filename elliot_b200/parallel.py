@@ -46,6 +46,11 @@ class ReplicatedTableSync:
         self._delta = delta_fn or ops.table_delta_f32
         self._apply = apply_fn or ops.table_apply_delta_f32
 
+    def reset(self):
+        """Re-baseline on the tables' current contents (they must already agree across ranks)."""
+        for t, p in zip(self.tables, self.prev):
+            p.copy_(t)
+
     def sync(self):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         scale = 1.0 / world if self.reduce == "mean" else 1.0
@@ -121,6 +126,12 @@ class OverlappedTableSync:
     def flush(self):
         """Apply the outstanding round (end of training / before scoring)."""
         self._finish()
+
+    def reset(self):
+        """Flush, then re-baseline on the tables' current contents (they must already agree across ranks)."""
+        self._finish()
+        for t, p in zip(self.tables, self.prev):
+            p.copy_(t)
 
 
 class ShardedTable:

@@ -213,6 +213,14 @@ int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, in
 int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_sum, const float *delta_local, int64_t n,
                                   float scale, void *stream);
 
+/* SM partition for compute/collective overlap (no reference counterpart): creates a green context holding
+ * all but >= reserve_sms SMs of the current device (rounded to the driver's 8-SM granularity) and n_streams
+ * CUDA streams bound to it.  Kernels launched on those streams run only inside the partition, so a collective
+ * (NCCL) kernel on an ordinary stream always finds the SMs left out.  *granted_sms = SMs in the partition; pass
+ * (device SMs - granted) as the reserve bits of eb_bpr_step_*'s flags so the persistent grid is sized to it.
+ * The context lives until process exit. */
+int eb_partition_streams_create(int reserve_sms, int n_streams, void **streams, int *granted_sms);
+
 /* ------------------------------------------------------------------------
  * Dense layers (MultiVAE encoder/decoder, NeuMF MLP): bf16 tensor-core GEMM
  *   C[M][N] (fp32) = act(alpha * A[M][K] . B[N][K]^T + bias[N])      act: 0 none, 1 tanh, 2 relu
