@@ -14,6 +14,7 @@ Rank 0 prints ONE JSON line (contract in the task statement).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -403,6 +404,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     score_ms = t.item()
 
+    # ---- metrics on the device: the top-10 tensor goes straight into eb_eval_topk_f64
+    # (nDCG/HR/Precision/Recall against a synthetic 20-relevant-items-per-user test CSR); timed with the scoring call
+    TE = 20
+    ge = torch.Generator(device=dev); ge.manual_seed(77 + rank)
+    te_items, _ = torch.sort(torch.randint(0, N_ITEMS, (S_USERS, TE), device=dev, generator=ge, dtype=torch.int32), dim=1)
+    te_indptr = torch.arange(0, (S_USERS + 1) * TE, TE, dtype=torch.int64, device=dev)
+    te_gain = torch.ones(S_USERS * TE, dtype=torch.float64, device=dev)
+    disc = torch.tensor([math.log(2) / math.log(r + 2) for r in range(10)], dtype=torch.float64, device=dev)
+    idcg = torch.full((S_USERS,), float(disc.sum().item()), dtype=torch.float64, device=dev)
+    eval_args = (te_indptr, te_items.reshape(-1).contiguous(), te_gain, idcg, disc)
+    ev_out, _ = ops.eval_topk(si, 10, *eval_args)
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(SREP):
+        si, sv, sst = ops.score_topk_tc(U, V, b, D, 10, indptr, indices, user_begin=0, n_sel=S_USERS)
+        ev_out, _ = ops.eval_topk(si, 10, *eval_args)
+    s1.record(); torch.cuda.synchronize()
+    t = torch.tensor([s0.elapsed_time(s1) / SREP], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    score_eval_ms = t.item()
+    ev_host = ev_out.cpu().tolist()
+
     # same kernel on a per-GPU slice of BASELINE.json configs[4] (20M users x 2M items, d=128, k=10, 8 GPUs):
     # V replicated (2M x 128), users sharded; 37 888 users of this rank's shard are scored per call
     C5_ITEMS, C5_D = 2_000_000, 128
@@ -466,6 +490,10 @@ def main():
                     "config": {"workload": f"{S_USERS} users/GPU x {N_ITEMS} items, d={D}, k=10, item bias + train mask "
                                            "(~100 items/user), tcgen05 bf16 mainloop + exact fp32 re-rank",
                                "rechecked_users": sst["rechecked"]},
+                    "with_device_metrics": {"value": S_USERS * world / (score_eval_ms * 1e-3), "unit": "users/s",
+                                            "what": "scoring + eb_eval_topk_f64 (nDCG/HR/Precision/Recall@10 vs 20 relevant "
+                                                    "items/user) per call; metrics never leave the GPU as lists",
+                                            "ndcg_at_10_rank0": ev_host[1] / max(ev_host[0], 1.0)},
                     "ms": score_ms,
                     "roofline": {"bound": "tensor", "achieved": 2.0 * D * N_ITEMS * S_USERS / (score_ms * 1e-3) / 1e12,
                                  "peak": load_peaks()[1], "unit": "TFLOP/s",

@@ -69,6 +69,9 @@ SIGNATURES = {
                                      c_void, c_void, c_void, c_void]),
     "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_f32, c_void]),
+    "eb_eval_topk_workspace_bytes": (c_size, [c_i64, c_int]),
+    "eb_eval_topk_f64": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
+                         c_void, c_size, c_void]),
     "eb_partition_streams_create": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(c_int)]),
     "eb_table_apply_delta_late_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),

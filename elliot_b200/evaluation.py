@@ -4,7 +4,11 @@ hit_rate.py, precision.py, recall.py), vectorised over (users x k) index arrays.
 
 The reference Evaluator is the parity judge and is NOT re-implemented in breadth (SURVEY.md §2
 #23 out of scope): tests/test_host_parity.py checks these four against numbers the reference's
-own Evaluator produced on the same lists (tests/golden)."""
+own Evaluator produced on the same lists (tests/golden).
+
+`eval_tensors` is the device path: the top-k index tensor written by the scoring kernels is
+scored against the test set by `eb_eval_topk_f64` without ever becoming Python tuples; same definitions, same
+numbers (fp64; summation order differs, <= 1e-12 relative)."""
 import math
 
 import numpy as np
@@ -39,6 +43,57 @@ class Evaluator:
             for slot, which in ((0, "val"), (1, "test")):
                 cs = self._sets[which]
                 res[which] = None if cs is None else self._eval_dict(recommendations[slot], cs, k)
+            if res["val"] is None:
+                res["val"] = res["test"]
+            if res["test"] is None:
+                res["test"] = res["val"]
+            out[k] = {"val_results": res["val"], "val_statistical_results": {},
+                      "test_results": res["test"], "test_statistical_results": {}}
+        return out
+
+    # ---- device path ---------------------------------------------------------------------------
+    def _device_set(self, which, k, device):
+        """Item-sorted relevant-item CSR + per-user IDCG@k + discounts on `device` (cached)."""
+        import torch
+        key = (which, k, str(device))
+        cache = self.__dict__.setdefault("_dev_sets", {})
+        if key in cache:
+            return cache[key]
+        cs = self._sets[which]
+        if cs is None:
+            cache[key] = None
+            return None
+        indptr, idx, gain = cs
+        n = len(indptr) - 1
+        rows = np.repeat(np.arange(n), np.diff(indptr))
+        disc = np.array([math.log(2) / math.log(r + 2) for r in range(k)])      # relevance.py:55
+        by_gain = np.lexsort((-gain, rows))                                      # ideal ranking per user
+        rank = np.arange(len(rows)) - indptr[rows]
+        top = rank < k
+        idcg = np.bincount(rows[top], weights=gain[by_gain][top] * disc[rank[top]], minlength=n)
+        by_item = np.lexsort((idx, rows))                                        # lookup rows sorted by item id
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dt)
+        cache[key] = (t(indptr, torch.int64), t(idx[by_item], torch.int32), t(gain[by_item], torch.float64),
+                      t(idcg, torch.float64), t(disc, torch.float64))
+        return cache[key]
+
+    def eval_tensors(self, idx, users=None):
+        """Same result structure as eval(), from a device (rows x top_k) int32 tensor of PRIVATE item ids
+        (-1 = empty), row r = private user r (or users[r])."""
+        from . import ops
+        out = {}
+        for k in self._k:
+            res = {}
+            for which in ("val", "test"):
+                ds = self._device_set(which, k, idx.device)
+                if ds is None:
+                    res[which] = None
+                    continue
+                sums, _ = ops.eval_topk(idx, k, *ds, users=users)
+                sums = sums.cpu().numpy()
+                n = sums[0]
+                vals = dict(zip(("nDCG", "HR", "Precision", "Recall"), (sums[1:] / n if n else np.zeros(4)).tolist()))
+                res[which] = {m: vals[m] for m in self._metrics}
             if res["val"] is None:
                 res["val"] = res["test"]
             if res["test"] is None:

@@ -392,6 +392,35 @@ def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local, scale=1.0):
                                                   float(scale), _stream(cur)))
 
 
+_eval_ws = None
+
+
+def eval_topk(topk_idx, k, rel_indptr, rel_items, rel_gains, idcg, discount, users=None, per_user=False):
+    """Accuracy metrics of a (rows x >=k) int32 top-k index tensor against an item-sorted relevant-item CSR
+    (evaluator.py:117-147 semantics).  Returns (out, per_user): out = device double[5]
+    {evaluated users, sum nDCG, sum HR, sum Precision, sum Recall}; per_user = (rows x 4) or None."""
+    global _eval_ws
+    _need_cuda(topk_idx, rel_indptr, rel_items, rel_gains, idcg, discount, users)
+    assert topk_idx.dtype == torch.int32 and topk_idx.stride(1) == 1 and topk_idx.shape[1] >= k
+    assert rel_indptr.dtype == torch.int64 and rel_items.dtype == torch.int32
+    assert rel_gains.dtype == torch.float64 and idcg.dtype == torch.float64 and discount.dtype == torch.float64
+    assert discount.numel() >= k
+    n = topk_idx.shape[0]
+    if users is not None:
+        _chk_idx(users); assert users.numel() == n
+    dev = topk_idx.device
+    out = torch.empty(5, dtype=torch.float64, device=dev)
+    pu = torch.empty(n, 4, dtype=torch.float64, device=dev) if per_user else None
+    need = lib().eb_eval_topk_workspace_bytes(n, k)
+    if _eval_ws is None or _eval_ws.numel() < need or _eval_ws.device != dev:
+        _eval_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().eb_eval_topk_f64(_ptr(topk_idx), n, topk_idx.stride(0), k, _ptr(users), _ptr(rel_indptr), _ptr(rel_items),
+                                     _ptr(rel_gains), _ptr(idcg), _ptr(discount), _ptr(pu), _ptr(out), _ptr(_eval_ws),
+                                     _eval_ws.numel(), _stream(topk_idx)))
+    return out, pu
+
+
 def partition_streams(device, reserve_sms, n_streams=1):
     """Streams bound to a green context that leaves >= reserve_sms SMs of `device` free (partition.cu).
     Returns (list of torch streams, SMs in the partition)."""

@@ -12,7 +12,9 @@ the CUDA kernels behind include/elliot_b200.h:
   mode "hogwild"          — throughput mode: fused Philox sampling + fp32 Hogwild step
       (eb_bpr_step_sampled_f32).  Same distribution, different stream; reports its own nDCG.
 
-Extra YAML keys (absent from the reference, both optional): `b200_mode`, `b200_batch`.
+Extra YAML keys (absent from the reference, all optional): `b200_mode`, `b200_batch`, `b200_eval`
+(`device`: metrics computed by `eb_eval_topk_f64` from the top-k tensor; `host`: the reference's dict path; default
+`host` in exact mode, `device` in hogwild mode).
 """
 import pickle
 
@@ -130,6 +132,8 @@ class BPRMF(RecMixin, BaseRecommenderModel):
         if self._mode not in ("exact", "hogwild"):
             raise Exception("b200_mode must be 'exact' or 'hogwild'")
         self._hog_batch = int(getattr(self._params, "b200_batch", 1 << 20))
+        if self._mode == "hogwild" and not hasattr(self._params, "b200_eval"):
+            self._params.b200_eval = "device"          # throughput mode: metrics straight from the top-k tensor
         self._batch_size = 1                                    # BPRMF.py:80 (YAML batch_size ignored)
         self._ratings = self._data.train_dict
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))

@@ -17,9 +17,18 @@ class RecMixin:
     def evaluate(self, it=None, loss=0):
         if it is not None and (it + 1) % self._validation_rate:
             return
-        recs = self.get_recommendations(self.evaluator.get_needed_recommendations())
+        on_device = (getattr(self._params, "b200_eval", "host") == "device" and hasattr(self, "get_recommendations_tensors")
+                     and hasattr(self.evaluator, "eval_tensors") and not self._save_recs and not self._negative_sampling)
         self._losses.append(loss)
-        self._results.append(self.evaluator.eval(recs))
+        if on_device:
+            # B200 extension: the (users x k) index tensor goes from the scoring kernel straight into the metric
+            # kernel; no {user: [(item, score)]} dicts are built (recommender_utils_mixin.py:84-88 / evaluator.py:117-147)
+            idx, _ = self.get_recommendations_tensors(self.evaluator.get_needed_recommendations())
+            recs = None
+            self._results.append(self.evaluator.eval_tensors(idx))
+        else:
+            recs = self.get_recommendations(self.evaluator.get_needed_recommendations())
+            self._results.append(self.evaluator.eval(recs))
         if it is not None:
             self.logger.info(f"Epoch {it + 1}/{self._epochs} loss {loss / (it + 1):.5f}")
         else:

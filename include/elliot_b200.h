@@ -213,6 +213,24 @@ int eb_table_apply_delta_f32(float *cur, float *prev, const float *delta_sum, in
 int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_sum, const float *delta_local, int64_t n,
                                   float scale, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Accuracy metrics of top-k lists, on the device.
+ * Replaces the per-user loops of Evaluator.eval (elliot/evaluation/evaluator.py:117-147) for nDCG
+ * (ndcg.py:68-125; discount relevance.py:55, gains relevance.py:80-82), HR, Precision, Recall.
+ * topk_idx[n_rows][ld]: private item ids, -1 = empty slot (as written by eb_score_topk_*); users (optional):
+ * private user id of each row (NULL = row r is user r).  rel_indptr/rel_items/rel_gains: CSR over private
+ * users of the relevant test items, rows sorted by item id (items absent from training carry id -1: they
+ * count for Recall/IDCG but can never be hit).  idcg[u]: ideal DCG@k of user u; discount[k]: ln2/ln(r+2).
+ * Users without relevant items are skipped (evaluator.py:121).
+ * out[5] (device) = {evaluated users, sum nDCG, sum HR, sum Precision, sum Recall}: fp64, deterministic.
+ * per_user (optional, device double[n_rows][4]): the per-user values (NaN for skipped users).
+ * ------------------------------------------------------------------------ */
+size_t eb_eval_topk_workspace_bytes(int64_t n_rows, int k);
+int eb_eval_topk_f64(const int32_t *topk_idx, int64_t n_rows, int ld, int k, const int32_t *users,
+                     const int64_t *rel_indptr, const int32_t *rel_items, const double *rel_gains,
+                     const double *idcg, const double *discount, double *per_user, double *out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* SM partition for compute/collective overlap (no reference counterpart): creates a green context holding
  * all but >= reserve_sms SMs of the current device (rounded to the driver's 8-SM granularity) and n_streams
  * CUDA streams bound to it.  Kernels launched on those streams run only inside the partition, so a collective

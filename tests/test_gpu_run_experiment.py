@@ -71,6 +71,19 @@ def test_yaml_driven_bprmf_equals_reference_run(tmp_path, case):
         assert np.abs(st["_user_factors"] - g["U"]).max() < 1e-12
 
 
+@pytest.mark.parametrize("case", ["tiny", "small"])
+def test_device_evaluation_gives_the_reference_metrics(tmp_path, case):
+    """b200_eval: device — the top-k tensor goes straight into eb_eval_topk_f64 (no rec dicts); the YAML-driven exact
+    run must still report the reference Evaluator's numbers."""
+    from elliot_b200 import run_experiment
+    g = dict(np.load(os.path.join(GOLDEN, f"bprmf_{case}.npz")))
+    res = run_experiment(_write_case(tmp_path, g, {"b200_eval": "device", "meta": {"save_recs": False, "save_weights": False}}))
+    k = int(g["k"])
+    want = dict(zip(g["metric_names"].tolist(), g["metric_vals"].tolist()))
+    for m in want:
+        assert abs(res[0]["test_results"][k][m] - want[m]) < 1e-12, (m, res[0]["test_results"][k][m], want[m])
+
+
 def test_hogwild_mode_trains_and_ranks(tmp_path):
     """Throughput mode through the same YAML: different stream, so only sanity + quality:
     nDCG@10 after 30 epochs must beat the untrained model by a wide margin."""
