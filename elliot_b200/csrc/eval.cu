@@ -99,13 +99,14 @@ extern "C" int eb_eval_topk_f64(const int32_t *topk_idx, int64_t n_rows, int ld,
                                 const double *idcg, const double *discount, double *per_user, double *out,
                                 void *workspace, size_t workspace_bytes, void *stream) {
     using namespace eb;
-    EB_ARG(topk_idx && rel_indptr && rel_items && rel_gains && idcg && discount && out, "null pointer");
+    EB_ARG(out, "null output pointer");
     EB_ARG(n_rows >= 0 && k >= 1 && k <= 1024 && ld >= k, "bad shape (n_rows=%lld k=%d ld=%d)", (long long)n_rows, k, ld);
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_rows == 0) {
+    if (n_rows == 0) {                                          // empty list set: nothing evaluated
         EB_CUDA(cudaMemsetAsync(out, 0, EVAL_NOUT * sizeof(double), st));
         return EB_OK;
     }
+    EB_ARG(topk_idx && rel_indptr && rel_items && rel_gains && idcg && discount, "null pointer");
     if (workspace_bytes < eb_eval_topk_workspace_bytes(n_rows, k) || !workspace)
         return set_err(EB_ERR_WORKSPACE, "eval workspace too small: need %zu bytes", eb_eval_topk_workspace_bytes(n_rows, k));
     const int G = eval_group(k);
