@@ -392,6 +392,38 @@ def table_apply_delta_late_f32(cur, prev, delta_sum, delta_local, scale=1.0):
                                                   float(scale), _stream(cur)))
 
 
+def mf_pointwise_exact_f64(U, V, ub, ib, gb, d, su, si, sr, lr, reg, batch=100000, batch_loss=None):
+    """MF2020 train_step over an ordered sample list, sequentially consistent fp64 (MF_model.py:80-112)."""
+    _need_cuda(U, V, ub, ib, gb, su, si, sr, batch_loss)
+    _chk_idx(su, si, sr)
+    for t in (U, V, ub, ib, gb):
+        assert t.dtype == torch.float64
+    assert U.stride(1) == 1 and V.stride(1) == 1 and U.stride(0) == V.stride(0) and ub.is_contiguous() and ib.is_contiguous()
+    n = su.numel()
+    if batch_loss is not None:
+        assert batch_loss.dtype == torch.float64 and batch_loss.numel() >= (n + batch - 1) // batch
+    with torch.cuda.device(U.device):
+        check(lib().eb_mf_pointwise_exact_f64(_ptr(U), _ptr(V), _ptr(ub), _ptr(ib), _ptr(gb), d, U.stride(0), _ptr(su), _ptr(si),
+                                              _ptr(sr), n, lr, reg, batch, _ptr(batch_loss), _stream(U)))
+
+
+def mf_pointwise_step_f32(U, V, ub, ib, gb, d, pos_u, pos_i, m, n_items, seed, epoch, lr, reg, loss=None, out=None):
+    """MF2020 throughput mode: one epoch (every positive + m uniform negatives) per launch, fp32 Hogwild."""
+    _need_cuda(U, V, ub, ib, gb, pos_u, pos_i, loss)
+    _chk_idx(pos_u, pos_i)
+    for t in (U, V, ub, ib, gb):
+        assert t.dtype == torch.float32
+    assert U.stride(1) == 1 and V.stride(1) == 1 and U.stride(0) == V.stride(0)
+    ou = oi = orr = None
+    if out is not None:
+        ou, oi, orr = out
+        _need_cuda(ou, oi, orr); _chk_idx(ou, oi, orr)
+    with torch.cuda.device(U.device):
+        check(lib().eb_mf_pointwise_step_f32(_ptr(U), _ptr(V), _ptr(ub), _ptr(ib), _ptr(gb), d, U.stride(0), _ptr(pos_u), _ptr(pos_i),
+                                             pos_u.numel(), m, n_items, seed, epoch, lr, reg, _ptr(loss), _ptr(ou), _ptr(oi),
+                                             _ptr(orr), _stream(U)))
+
+
 _eval_ws = None
 
 

@@ -10,4 +10,4 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
 from elliot_b200.recommender import *  # noqa: F401,F403,E402
-from elliot_b200.recommender import BPRMF, BPRMF_batch, MultiVAE, NeuMF  # noqa: F401,E402
+from elliot_b200.recommender import BPRMF, BPRMF_batch, MF2020, MultiVAE, NeuMF  # noqa: F401,E402

@@ -4,3 +4,4 @@ from .bprmf import BPRMF, MFModel  # noqa: F401
 from .bprmf_batch import BPRMF_batch, BPRMFBatchModel  # noqa: F401
 from .multi_vae import MultiVAE, VariationalAutoEncoder  # noqa: F401
 from .neumf import NeuMF, NeuralMatrixFactorizationModel  # noqa: F401
+from .mf2020 import MF2020, MF2020Model  # noqa: F401

@@ -214,6 +214,30 @@ int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_su
                                   float scale, void *stream);
 
 /* ------------------------------------------------------------------------
+ * MF2020: pointwise logistic matrix factorisation (sibling model on the same gather/dot/scatter shape).
+ * Replaces MFModel.train_step (elliot/recommender/latent_factor_models/MF2020/MF_model.py:80-112):
+ *   pred = gb + ub[u] + ib[i] + U[u].V[i]; grad = rating - sigmoid(pred);
+ *   U[u] += lr(grad V[i] - reg U[u]); V[i] += lr(grad U'[u] - reg V[i]) (U' already updated: view aliasing);
+ *   ub[u], ib[i], gb += lr(grad - reg .)
+ * eb_mf_pointwise_exact_f64: the reference's order, fp64 — the global bias makes every sample depend on the
+ *   previous one, so one warp walks the list (software-pipelined).  su/si/sr: the epoch's (user, item, label)
+ *   list as produced by custom_sampler_rendle.Sampler.step; batch_loss[t / batch] (optional) = sum of this_loss
+ *   over each `batch` consecutive samples (MF.py:120-124 divides by len(batch) itself); global_bias: device double[1].
+ * eb_mf_pointwise_step_f32: throughput mode, one whole epoch per launch: every positive (pos_u[p], pos_i[p], 1)
+ *   plus m uniform items (pos_u[p], j, 0) — not rejected against the train set, like custom_sampler_rendle.py:66-69 —
+ *   visited in a pseudo-random order (affine permutation re-drawn per epoch instead of random.sample), Philox
+ *   negatives keyed by (seed, epoch), fp32 vector atomics, global bias moved once per warp.
+ *   out_u/out_i/out_r (optional, n_pos*(1+m) each): the samples in visiting order.  loss (optional): += sum this_loss.
+ * ------------------------------------------------------------------------ */
+int eb_mf_pointwise_exact_f64(double *U, double *V, double *user_bias, double *item_bias, double *global_bias,
+                              int d, int ld, const int32_t *su, const int32_t *si, const int32_t *sr, int64_t n,
+                              double lr, double reg, int64_t batch, double *batch_loss, void *stream);
+int eb_mf_pointwise_step_f32(float *U, float *V, float *user_bias, float *item_bias, float *global_bias, int d, int ld,
+                             const int32_t *pos_u, const int32_t *pos_i, int64_t n_pos, int m, int32_t n_items,
+                             uint64_t seed, uint64_t epoch, float lr, float reg, double *loss,
+                             int32_t *out_u, int32_t *out_i, int32_t *out_r, void *stream);
+
+/* ------------------------------------------------------------------------
  * Accuracy metrics of top-k lists, on the device.
  * Replaces the per-user loops of Evaluator.eval (elliot/evaluation/evaluator.py:117-147) for nDCG
  * (ndcg.py:68-125; discount relevance.py:55, gains relevance.py:80-82), HR, Precision, Recall.

@@ -121,3 +121,34 @@ def user_topk(U, V, b, mask_indptr, mask_indices, users, k):
                         None if mask_indptr is None else _p(mask_indices),
                         _p(users), ctypes.c_int64(len(users)), ctypes.c_int(k), _p(idx), _p(val))
     return idx, val
+
+
+def mf2020_update_seq(U, V, ub, ib, gb, su, si, sr, lr, reg, batch=100000):
+    """MF2020 MFModel.train_step over a whole epoch's sample list, in order (MF_model.py:80-112).
+    Updates U, V, ub, ib in place; returns (new global bias, per-batch loss sums)."""
+    n = len(su)
+    g = ctypes.c_double(gb)
+    bl = np.zeros((n + batch - 1) // batch if n else 0, dtype=np.float64)
+    for a in (U, V, ub, ib):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    su, si, sr = (np.ascontiguousarray(x, dtype=np.int32) for x in (su, si, sr))
+    lib().orc_mf2020_update_seq(_p(U), _p(V), _p(ub), _p(ib), ctypes.byref(g), ctypes.c_int(U.shape[1]),
+                                ctypes.c_double(lr), ctypes.c_double(reg), _p(su), _p(si), _p(sr), ctypes.c_int64(n),
+                                ctypes.c_int64(batch), _p(bl))
+    return g.value, bl
+
+
+def mf2020_epoch_samples(np_rs, py_rng, pos_u, pos_i, n_items, m):
+    """custom_sampler_rendle.Sampler.step (MF2020/custom_sampler_rendle.py:29-85): every positive (u, i, 1) in
+    sp_i_train.nonzero() order followed by m uniform items (u, randint(n_items), 0) — NOT rejected against the
+    train set — then one random.sample permutation of the whole list.  np_rs: numpy legacy RandomState carrying
+    the process's global stream position; py_rng: random.Random at the reference's position."""
+    n = len(pos_u)
+    mat = np.empty((n * (1 + m), 3), dtype=np.int32)
+    mat[::1 + m, 0] = pos_u; mat[::1 + m, 1] = pos_i; mat[::1 + m, 2] = 1
+    if m:
+        neg = np_rs.randint(n_items, size=n * m).reshape(n, m)
+        for q in range(m):
+            mat[1 + q::1 + m, 0] = pos_u; mat[1 + q::1 + m, 1] = neg[:, q]; mat[1 + q::1 + m, 2] = 0
+    perm = py_rng.sample(range(len(mat)), len(mat))
+    return mat[perm]

@@ -266,3 +266,50 @@ void orc_user_topk(const double *U, const double *V, const double *item_bias,
 }
 
 size_t orc_rng_size(void) { return sizeof(orc_rng); }
+
+/* ---------------------------------------------------------------------------
+ * MF2020 (pointwise logistic MF of "NCF vs MF revisited").
+ * MFModel.train_step — elliot/recommender/latent_factor_models/MF2020/MF_model.py:80-112:
+ *   pred = gb + ub[u] + ib[i] + U[u].V[i];  numerically split sigmoid/loss (:94-101);
+ *   grad = rating - sigmoid;
+ *   U[u] += lr (grad V[i] - reg U[u])          (uf_ is a VIEW: updated in place, :105)
+ *   V[i] += lr (grad U'[u] - reg V[i])         (reads the UPDATED user row, :106)
+ *   ub[u] += lr (grad - reg ub_old); ib[i] += lr (grad - reg ib_old); gb += lr (grad - reg gb_old)
+ * batch_loss[t / batch] accumulates this_loss in sample order (MF.py:123: loss += train_step(batch)/len(batch)
+ * is left to the caller).  Strictly sequential: every sample reads and writes the global bias. */
+void orc_mf2020_update_seq(double *U, double *V, double *ub, double *ib, double *gb, int d, double lr, double reg,
+                           const int32_t *su, const int32_t *si, const int32_t *sr, int64_t n, int64_t batch,
+                           double *batch_loss) {
+    double g = *gb;
+    for (int64_t t = 0; t < n; t++) {
+        double *u = U + (int64_t)su[t] * d;
+        double *v = V + (int64_t)si[t] * d;
+        const double r = (double)sr[t];
+        const double bu = ub[su[t]], bi = ib[si[t]];
+        double dot = 0.0;
+        for (int k = 0; k < d; k++) dot += u[k] * v[k];
+        const double pred = g + bu + bi + dot;
+        double sig, loss;
+        if (pred > 0) {
+            const double ope = 1.0 + exp(-pred);
+            sig = 1.0 / ope;
+            loss = log(ope) + (1.0 - r) * pred;
+        } else {
+            const double e = exp(pred);
+            sig = e / (1.0 + e);
+            loss = -r * pred + log(1.0 + e);
+        }
+        const double grad = r - sig;
+        for (int k = 0; k < d; k++) {
+            const double uk = u[k], vk = v[k];
+            const double un = uk + lr * (grad * vk - reg * uk);
+            u[k] = un;
+            v[k] = vk + lr * (grad * un - reg * vk);
+        }
+        ub[su[t]] = bu + lr * (grad - reg * bu);
+        ib[si[t]] = bi + lr * (grad - reg * bi);
+        g += lr * (grad - reg * g);
+        if (batch_loss) batch_loss[t / batch] += loss;
+    }
+    *gb = g;
+}

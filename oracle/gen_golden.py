@@ -204,8 +204,61 @@ def make_sampler_cases():
     print("samplers", {k: v.shape for k, v in out.items()})
 
 
+def make_mf2020_case(name, d, seed, m, epochs, lr, reg, k):
+    """Reference MF2020 (latent_factor_models/MF2020/MF_model.py + custom_sampler_rendle.py) on the train/test split
+    of bprmf_<name>.npz, with the construction order of MF.py:58-80 under @init_charger
+    (base_recommender_model.py:149-150): seed np/random -> Sampler (seeds again) -> MFModel (seeds np, draws the
+    tables) -> epochs of sampler.step(100000) / train_step."""
+    import random
+    sys.path.insert(0, REF)
+    logging.disable(logging.CRITICAL)
+    ps = _load("ref_mf2020_sampler", "elliot/recommender/latent_factor_models/MF2020/custom_sampler_rendle.py")
+    mm = _load("ref_mf2020_model", "elliot/recommender/latent_factor_models/MF2020/MF_model.py")
+    import elliot.dataset.dataset as ds
+    from elliot.evaluation.evaluator import Evaluator
+    g = np.load(os.path.join(OUT, f"bprmf_{name}.npz"))
+    f = lambda a: pd.DataFrame({"userId": a[:, 0].astype(np.int64), "itemId": a[:, 1].astype(np.int64), "rating": a[:, 2]})
+    config = SimpleNamespace(config_test=True, align_side_with_train=False, top_k=k,
+                             evaluation=SimpleNamespace(simple_metrics=["nDCG", "HR", "Precision", "Recall"],
+                                                        relevance_threshold=0, paired_ttest=False, cutoffs=[k]))
+    data = ds.DataSet(config, (f(g["train"]), f(g["test"])), SimpleNamespace())
+    np.random.seed(seed); random.seed(seed)                                   # init_charger
+    sampler = ps.Sampler(data.i_train_dict, m, data.sp_i_train, seed)
+    model = mm.MFModel(d, data, lr, reg, seed)
+    U0, V0 = model._user_factors.copy(), model._item_factors.copy()
+    pos = np.array([(int(a), int(b)) for a, b, _ in sampler._positive_pairs], dtype=np.int32)
+    samples, batch_losses, epoch_loss = [], [], []
+    for ep in range(epochs):
+        loss, ep_rows, bl = 0.0, [], []
+        for batch in sampler.step(100000):
+            ep_rows.append(batch.copy())
+            s = model.train_step(batch)
+            bl.append(float(s)); loss += s / len(batch)
+        samples.append(np.concatenate(ep_rows)); batch_losses.append(np.array(bl)); epoch_loss.append(loss)
+    model.prepare_predictions()
+    mask = data.allunrated_mask
+    rec_idx = np.full((len(data.users), k), -1, dtype=np.int32); rec_val = np.full((len(data.users), k), -np.inf)
+    recs = {}
+    for pu, u_pub in enumerate(data.users):
+        r = model.get_user_predictions(u_pub, mask, k)
+        recs[u_pub] = r
+        for q, (it, sc) in enumerate(r):
+            rec_idx[pu, q] = data.public_items[it]; rec_val[pu, q] = sc
+    metrics = Evaluator(data, SimpleNamespace(meta=SimpleNamespace())).eval((recs, recs))[k]["test_results"]
+    out = {f"samples_ep{e}": samples[e] for e in range(epochs)}
+    out.update({f"batch_loss_ep{e}": batch_losses[e] for e in range(epochs)})
+    np.savez_compressed(os.path.join(OUT, f"mf2020_{name}.npz"), d=d, seed=seed, m=m, epochs=epochs, lr=lr, reg=reg, k=k,
+                        positives=pos, U0=U0, V0=V0, U=model._user_factors, V=model._item_factors,
+                        ub=model._user_bias, ib=model._item_bias, gb=model._global_bias, epoch_loss=np.array(epoch_loss),
+                        rec_idx=rec_idx, rec_val=rec_val, metric_names=np.array(sorted(metrics)),
+                        metric_vals=np.array([metrics[x] for x in sorted(metrics)]), **out)
+    print("mf2020", name, "samples/epoch", len(samples[0]), "gb", model._global_bias, {x: round(v, 6) for x, v in metrics.items()})
+
+
 if __name__ == "__main__":
     make_split_case()
     make_case("tiny", n_users=60, n_items=48, mean_pos=8, d=10, seed_data=1, model_seed=42, epochs=2, k=10)
     make_sampler_cases()
     make_case("small", n_users=400, n_items=300, mean_pos=20, d=64, seed_data=2, model_seed=7, epochs=2, k=10)
+    make_mf2020_case("tiny", d=10, seed=42, m=2, epochs=2, lr=0.05, reg=0.01, k=10)
+    make_mf2020_case("small", d=64, seed=7, m=3, epochs=2, lr=0.05, reg=0.005, k=10)

@@ -121,3 +121,20 @@ def test_multivae_epoch_order_replays_reference():
     random.seed(42)
     for ep in range(2):
         assert epoch_user_order(s["vae_perm"].shape[1]) == s["vae_perm"][ep].tolist()
+
+
+@pytest.mark.parametrize("case", ["tiny", "small"])
+def test_mf2020_sampler_replays_reference_epochs(case):
+    """RendleSampler (host side of MF2020 exact mode) against the reference's custom_sampler_rendle run: positives in
+    sp_i_train.nonzero() order, then the two epoch sample lists, item for item."""
+    from elliot_b200.recommender.mf2020 import RendleSampler
+    g = dict(np.load(os.path.join(GOLDEN, f"mf2020_{case}.npz")))
+    gb = dict(np.load(os.path.join(GOLDEN, f"bprmf_{case}.npz")))
+    data = DataSet(_config(int(g["k"])), _frames(gb))
+    rs = np.random.RandomState(int(g["seed"]))
+    U0 = rs.normal(0, 0.1, (data.num_users, int(g["d"]))); V0 = rs.normal(0, 0.1, (data.num_items, int(g["d"])))
+    assert np.array_equal(U0, g["U0"]) and np.array_equal(V0, g["V0"])
+    smp = RendleSampler(data.sp_i_train, int(g["m"]), int(g["seed"]), rs)
+    assert np.array_equal(np.stack([smp.pos_u, smp.pos_i], 1), g["positives"])
+    for ep in range(int(g["epochs"])):
+        assert np.array_equal(smp.epoch(), g[f"samples_ep{ep}"])

@@ -1,8 +1,13 @@
 """The oracle restatement (oracle/bprmf_oracle.c) against goldens minted from the reference's
 own code (oracle/gen_golden.py) and against numpy's legacy RandomState."""
+import os
+
 import numpy as np
+import pytest
 
 import oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def test_mt19937_raw_stream_matches_numpy():
@@ -94,3 +99,27 @@ def test_numpy_port_matches_golden(golden_tiny):
     got = np.array(got)
     assert np.array_equal(got[:, 0], g["tu"][:T]) and np.array_equal(got[:, 1], g["ti"][:T]) and np.array_equal(got[:, 2], g["tj"][:T])
     assert np.abs(m.P - g["U_ep1"]).max() < 1e-13 and np.abs(m.Q - g["V_ep1"]).max() < 1e-13
+
+
+# ---------------------------------------------------------------- MF2020 (pointwise, NumPy reference -> pinned)
+@pytest.mark.parametrize("case", ["tiny", "small"])
+def test_mf2020_oracle_matches_reference_run(case):
+    """oracle.mf2020_epoch_samples / mf2020_update_seq against the reference's own MF2020 run
+    (tests/golden/mf2020_<case>.npz minted by oracle/gen_golden.py): init bit-exact, sample lists bit-exact,
+    tables / biases / batch losses to 1e-12."""
+    import random
+    g = dict(np.load(os.path.join(GOLDEN, f"mf2020_{case}.npz")))
+    gb_ = dict(np.load(os.path.join(GOLDEN, f"bprmf_{case}.npz")))
+    nu, ni, d, seed, m = len(gb_["users"]), len(gb_["items"]), int(g["d"]), int(g["seed"]), int(g["m"])
+    rs = np.random.RandomState(seed); pr = random.Random(seed)
+    U = rs.normal(0, 0.1, (nu, d)); V = rs.normal(0, 0.1, (ni, d))
+    assert np.array_equal(U, g["U0"]) and np.array_equal(V, g["V0"])
+    ub, ib, gbias = np.zeros(nu), np.zeros(ni), 0.0
+    pos = g["positives"]
+    for ep in range(int(g["epochs"])):
+        smp = oracle.mf2020_epoch_samples(rs, pr, pos[:, 0], pos[:, 1], ni, m)
+        assert np.array_equal(smp, g[f"samples_ep{ep}"])
+        gbias, bl = oracle.mf2020_update_seq(U, V, ub, ib, gbias, smp[:, 0], smp[:, 1], smp[:, 2], float(g["lr"]), float(g["reg"]))
+        assert np.allclose(bl, g[f"batch_loss_ep{ep}"], rtol=1e-12, atol=0)
+    assert np.abs(U - g["U"]).max() < 1e-12 and np.abs(V - g["V"]).max() < 1e-12
+    assert np.abs(ub - g["ub"]).max() < 1e-12 and np.abs(ib - g["ib"]).max() < 1e-12 and abs(gbias - float(g["gb"])) < 1e-12
