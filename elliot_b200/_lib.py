@@ -72,7 +72,7 @@ SIGNATURES = {
     "eb_mf_pointwise_exact_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
                                   c_f64, c_f64, c_i64, c_void, c_void]),
     "eb_mf_pointwise_step_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_i64, c_int, c_i32,
-                                 c_u64, c_u64, c_f32, c_f32, c_void, c_void, c_void, c_void, c_void]),
+                                 c_u64, c_u64, c_i64, c_i64, c_f32, c_f32, c_void, c_void, c_void, c_void, c_void, c_void]),
     "eb_eval_topk_workspace_bytes": (c_size, [c_i64, c_int]),
     "eb_eval_topk_f64": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                          c_void, c_size, c_void]),

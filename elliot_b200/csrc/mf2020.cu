@@ -133,6 +133,8 @@ struct MfHogParams {
     int ld;
     const int32_t *pos_u, *pos_i;
     int64_t n_pos, n;          // n = n_pos * (1 + m) samples per epoch
+    int64_t s_begin, s_end;    // this launch covers epoch positions [s_begin, s_end)
+    double *gb_work;           // {sum grad, sum sig(1-sig), samples} of the launch
     int m;
     int32_t n_items;
     uint64_t seed, first, mul, add;
@@ -167,12 +169,12 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const MfHogParams p) {
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t ld = p.ld;
     const float gb0 = *p.gb;                                      // stale within the launch (Hogwild)
-    float loss_acc = 0.f, gsum = 0.f, gcnt = 0.f;
-    for (int64_t tile = warp_id; tile * 32 < p.n; tile += nwarps) {
-        const int64_t s = tile * 32 + lane;
+    float loss_acc = 0.f, gsum = 0.f, hsum = 0.f, gcnt = 0.f;
+    for (int64_t tile = warp_id; p.s_begin + tile * 32 < p.s_end; tile += nwarps) {
+        const int64_t s = p.s_begin + tile * 32 + lane;
         int u = -1, i = 0;
         float r = 0.f;
-        if (s < p.n) {
+        if (s < p.s_end) {
             mf_sample(p, s, u, i, r);
             if (p.out_u) { p.out_u[s] = u; p.out_i[s] = i; p.out_r[s] = (int32_t)r; }
         }
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const MfHogParams p) {
                     const float grad = rr[q] - sig;
                     if (gl == 0) {
                         loss_acc += fmaxf(pred, 0.f) - rr[q] * pred + __logf(1.f + e);
-                        gsum += grad; gcnt += 1.f;
+                        gsum += grad; hsum += sig * (1.f - sig); gcnt += 1.f;
                         red_add_f32(p.ub + cu[q], p.lr * (grad - p.reg * bu[q]));
                         red_add_f32(p.ib + ci[q], p.lr * (grad - p.reg * bi[q]));
                     }
@@ -237,12 +239,29 @@ __global__ void __launch_bounds__(256) mf_hogwild_kernel(const MfHogParams p) {
     for (int off = 16; off > 0; off >>= 1) {
         loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
         gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+        hsum += __shfl_xor_sync(0xffffffffu, hsum, off);
         gcnt += __shfl_xor_sync(0xffffffffu, gcnt, off);
     }
     if (lane == 0 && gcnt != 0.f) {
-        red_add_f32(p.gb, p.lr * (gsum - p.reg * gb0 * gcnt));     // one global-bias move per warp
+        atomicAdd(p.gb_work + 0, (double)gsum); atomicAdd(p.gb_work + 1, (double)hsum); atomicAdd(p.gb_work + 2, (double)gcnt);
         if (p.loss) atomicAdd(p.loss, (double)loss_acc);
     }
+}
+
+// The global bias is one scalar hit by EVERY sample: applying c stale gradients at once (gb += lr*sum) overshoots as soon
+// as lr*c*sig' > 2.  The reference takes c tiny sequential steps gb += lr (g_s(gb) - reg gb); linearising the
+// gradient around the launch's stale value, g_s(gb) ~ g_s(gb0) - sig'_s (gb - gb0), those steps integrate to
+//   gb = gb0 + (gbar - reg gb0) / (hbar + reg) * (1 - exp(-lr (hbar + reg) c)),   gbar = sum g / c, hbar = sum sig' / c,
+// which is the plain step for small lr*c and saturates at the launch's fixed point for large ones.
+__global__ void mf_global_bias_finish_kernel(float *gb, double *work, float lr, float reg) {
+    const double c = work[2];
+    if (c > 0) {
+        const double g0 = (double)*gb, gbar = work[0] / c, k = work[1] / c + (double)reg;
+        const double x = (double)lr * k * c;
+        const double gain = k > 1e-12 ? -expm1(-x) / k : (double)lr * c;
+        *gb = (float)(g0 + (gbar - (double)reg * g0) * gain);
+    }
+    work[0] = 0; work[1] = 0; work[2] = 0;
 }
 
 template <int DP>
@@ -250,11 +269,13 @@ static int launch_mf_hogwild(const MfHogParams &p, cudaStream_t st) {
     int per_sm = 0;
     EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mf_hogwild_kernel<DP>, 256, 0));
     if (per_sm < 1) per_sm = 1;
-    const int64_t tiles = (p.n + 31) / 32, want = (tiles + 7) / 8;
+    const int64_t tiles = (p.s_end - p.s_begin + 31) / 32, want = (tiles + 7) / 8;
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     mf_hogwild_kernel<DP><<<(unsigned)grid, 256, 0, st>>>(p);
+    EB_CUDA(cudaGetLastError());
+    mf_global_bias_finish_kernel<<<1, 1, 0, st>>>(p.gb, p.gb_work, p.lr, p.reg);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
@@ -284,17 +305,23 @@ extern "C" int eb_mf_pointwise_exact_f64(double *U, double *V, double *user_bias
 
 extern "C" int eb_mf_pointwise_step_f32(float *U, float *V, float *user_bias, float *item_bias, float *global_bias, int d, int ld,
                                         const int32_t *pos_u, const int32_t *pos_i, int64_t n_pos, int m, int32_t n_items,
-                                        uint64_t seed, uint64_t epoch, float lr, float reg, double *loss,
-                                        int32_t *out_u, int32_t *out_i, int32_t *out_r, void *stream) {
+                                        uint64_t seed, uint64_t epoch, int64_t first, int64_t count, float lr, float reg,
+                                        double *loss, double *gb_work, int32_t *out_u, int32_t *out_i, int32_t *out_r,
+                                        void *stream) {
     using namespace eb;
     EB_ARG(U && V && user_bias && item_bias && global_bias, "null table pointer");
     EB_ARG(d >= 1 && ld >= d, "need 1 <= d <= ld (d=%d ld=%d)", d, ld);
     EB_ARG(((uintptr_t)U % 16) == 0 && ((uintptr_t)V % 16) == 0, "tables must be 16-byte aligned");
     EB_ARG(n_pos >= 0 && m >= 0 && n_items >= 1, "bad n_pos / m / n_items");
     EB_ARG((out_u == nullptr) == (out_i == nullptr) && (out_u == nullptr) == (out_r == nullptr), "out_u/out_i/out_r go together");
-    if (n_pos == 0) return EB_OK;
+    EB_ARG(gb_work, "gb_work (device double[4], zero-initialised) is required");
+    const int64_t n_epoch = n_pos * (int64_t)(1 + m);
+    EB_ARG(first >= 0 && count >= 0 && first + count <= n_epoch, "samples [%lld, %lld) outside the epoch of %lld",
+           (long long)first, (long long)(first + count), (long long)n_epoch);
+    if (count == 0) return EB_OK;
     EB_ARG(pos_u && pos_i, "null positives");
     MfHogParams p{};
+    p.s_begin = first; p.s_end = first + count; p.gb_work = gb_work;
     p.U = U; p.V = V; p.ub = user_bias; p.ib = item_bias; p.gb = global_bias; p.ld = ld;
     p.pos_u = pos_u; p.pos_i = pos_i; p.n_pos = n_pos; p.m = m; p.n = n_pos * (int64_t)(1 + m); p.n_items = n_items;
     p.seed = seed; p.first = epoch * (uint64_t)p.n;

@@ -407,8 +407,13 @@ def mf_pointwise_exact_f64(U, V, ub, ib, gb, d, su, si, sr, lr, reg, batch=10000
                                               _ptr(sr), n, lr, reg, batch, _ptr(batch_loss), _stream(U)))
 
 
-def mf_pointwise_step_f32(U, V, ub, ib, gb, d, pos_u, pos_i, m, n_items, seed, epoch, lr, reg, loss=None, out=None):
-    """MF2020 throughput mode: one epoch (every positive + m uniform negatives) per launch, fp32 Hogwild."""
+_mf_gb_work = {}
+
+
+def mf_pointwise_step_f32(U, V, ub, ib, gb, d, pos_u, pos_i, m, n_items, seed, epoch, lr, reg, loss=None, out=None,
+                          first=0, count=None):
+    """MF2020 throughput mode: positions [first, first+count) of the epoch's sample list (every positive + m uniform
+    negatives, pseudo-randomly ordered) in one launch, fp32 Hogwild; count=None -> to the end of the epoch."""
     _need_cuda(U, V, ub, ib, gb, pos_u, pos_i, loss)
     _chk_idx(pos_u, pos_i)
     for t in (U, V, ub, ib, gb):
@@ -418,10 +423,16 @@ def mf_pointwise_step_f32(U, V, ub, ib, gb, d, pos_u, pos_i, m, n_items, seed, e
     if out is not None:
         ou, oi, orr = out
         _need_cuda(ou, oi, orr); _chk_idx(ou, oi, orr)
+    n_epoch = pos_u.numel() * (1 + m)
+    if count is None:
+        count = n_epoch - first
+    work = _mf_gb_work.get(U.device)
+    if work is None:
+        work = _mf_gb_work[U.device] = torch.zeros(4, dtype=torch.float64, device=U.device)
     with torch.cuda.device(U.device):
         check(lib().eb_mf_pointwise_step_f32(_ptr(U), _ptr(V), _ptr(ub), _ptr(ib), _ptr(gb), d, U.stride(0), _ptr(pos_u), _ptr(pos_i),
-                                             pos_u.numel(), m, n_items, seed, epoch, lr, reg, _ptr(loss), _ptr(ou), _ptr(oi),
-                                             _ptr(orr), _stream(U)))
+                                             pos_u.numel(), m, n_items, seed, epoch, first, count, lr, reg, _ptr(loss), _ptr(work),
+                                             _ptr(ou), _ptr(oi), _ptr(orr), _stream(U)))
 
 
 _eval_ws = None

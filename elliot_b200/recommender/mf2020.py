@@ -107,7 +107,8 @@ class MF2020(RecMixin, BaseRecommenderModel):
     r"""Matrix Factorization as in "NCF vs. MF Revisited" (https://dl.acm.org/doi/pdf/10.1145/3383313.3412488) on B200.
 
     YAML block identical to the reference's (MF.py:41-52): MF2020: {meta: {...}, epochs, factors, lr, reg, m};
-    optional B200 keys `b200_mode` (exact | hogwild), `b200_eval`, `b200_device`.
+    optional B200 keys `b200_mode` (exact | hogwild), `b200_batch` (samples per Hogwild launch), `b200_eval`,
+    `b200_device`.
     """
 
     @init_charger
@@ -122,6 +123,7 @@ class MF2020(RecMixin, BaseRecommenderModel):
         self._mode = getattr(self._params, "b200_mode", "exact")
         if self._mode not in ("exact", "hogwild"):
             raise Exception("b200_mode must be 'exact' or 'hogwild'")
+        self._hog_batch = int(getattr(self._params, "b200_batch", 1 << 20))   # samples per Hogwild launch
         if self._mode == "hogwild" and not hasattr(self._params, "b200_eval"):
             self._params.b200_eval = "device"
         if not torch.cuda.is_available():
@@ -183,9 +185,12 @@ class MF2020(RecMixin, BaseRecommenderModel):
             else:
                 self._loss_dev.zero_()
                 m = self._model
-                ops.mf_pointwise_step_f32(m.U, m.V, m.ub, m.ib, m.gb, self._factors, self._pos_u, self._pos_i, self._m,
-                                          self._sampler._nitems, self._seed, self._epoch_counter, self._learning_rate,
-                                          self._regularization, loss=self._loss_dev)
+                n = len(self._sampler.pos_u) * (1 + self._m)
+                for first in range(0, n, self._hog_batch):
+                    ops.mf_pointwise_step_f32(m.U, m.V, m.ub, m.ib, m.gb, self._factors, self._pos_u, self._pos_i, self._m,
+                                              self._sampler._nitems, self._seed, self._epoch_counter, self._learning_rate,
+                                              self._regularization, loss=self._loss_dev, first=first,
+                                              count=min(self._hog_batch, n - first))
                 self._epoch_counter += 1
                 n = len(self._sampler.pos_u) * (1 + self._m)
                 nb = (n + self._batch_size - 1) // self._batch_size

@@ -223,19 +223,22 @@ int eb_table_apply_delta_late_f32(float *cur, float *prev, const float *delta_su
  *   previous one, so one warp walks the list (software-pipelined).  su/si/sr: the epoch's (user, item, label)
  *   list as produced by custom_sampler_rendle.Sampler.step; batch_loss[t / batch] (optional) = sum of this_loss
  *   over each `batch` consecutive samples (MF.py:120-124 divides by len(batch) itself); global_bias: device double[1].
- * eb_mf_pointwise_step_f32: throughput mode, one whole epoch per launch: every positive (pos_u[p], pos_i[p], 1)
- *   plus m uniform items (pos_u[p], j, 0) — not rejected against the train set, like custom_sampler_rendle.py:66-69 —
- *   visited in a pseudo-random order (affine permutation re-drawn per epoch instead of random.sample), Philox
- *   negatives keyed by (seed, epoch), fp32 vector atomics, global bias moved once per warp.
- *   out_u/out_i/out_r (optional, n_pos*(1+m) each): the samples in visiting order.  loss (optional): += sum this_loss.
+ * eb_mf_pointwise_step_f32: throughput mode.  The epoch is the list of every positive (pos_u[p], pos_i[p], 1) plus m
+ *   uniform items (pos_u[p], j, 0) — not rejected against the train set, like custom_sampler_rendle.py:66-69 — in a
+ *   pseudo-random visiting order (affine permutation re-drawn per epoch instead of random.sample), Philox negatives
+ *   keyed by (seed, epoch); one launch applies positions [first, first+count) of it with fp32 vector atomics
+ *   (Hogwild: keep count small enough that a row is not hit by many stale updates).  The global bias, hit by every
+ *   sample, is advanced once per launch by the closed-form integral of the c sequential steps (see mf2020.cu);
+ *   gb_work: device double[4] scratch, zero before the first call, left zero.
+ *   out_u/out_i/out_r (optional, n_pos*(1+m) each, indexed by epoch position).  loss (optional): += sum this_loss.
  * ------------------------------------------------------------------------ */
 int eb_mf_pointwise_exact_f64(double *U, double *V, double *user_bias, double *item_bias, double *global_bias,
                               int d, int ld, const int32_t *su, const int32_t *si, const int32_t *sr, int64_t n,
                               double lr, double reg, int64_t batch, double *batch_loss, void *stream);
 int eb_mf_pointwise_step_f32(float *U, float *V, float *user_bias, float *item_bias, float *global_bias, int d, int ld,
                              const int32_t *pos_u, const int32_t *pos_i, int64_t n_pos, int m, int32_t n_items,
-                             uint64_t seed, uint64_t epoch, float lr, float reg, double *loss,
-                             int32_t *out_u, int32_t *out_i, int32_t *out_r, void *stream);
+                             uint64_t seed, uint64_t epoch, int64_t first, int64_t count, float lr, float reg, double *loss,
+                             double *gb_work, int32_t *out_u, int32_t *out_i, int32_t *out_r, void *stream);
 
 /* ------------------------------------------------------------------------
  * Accuracy metrics of top-k lists, on the device.
