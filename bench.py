@@ -449,6 +449,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     c5_ms = t.item()
     del U5, V5, b5, m5, k5, ix5
+
+    # ---- sibling model on the same gather/dot/scatter shape: MF2020 pointwise logistic step (N=1 only; C2 tables,
+    # the first 2^22 positions of an epoch over the train CSR's positives with m=1 uniform negative each)
+    mf_rate = None
+    if world == 1:
+        lens = (indptr[1:] - indptr[:-1])
+        pos_u = torch.repeat_interleave(torch.arange(N_USERS, dtype=torch.int32, device=dev), lens)
+        Um = U.clone(); Vm = V.clone()
+        ubm = torch.zeros(N_USERS, device=dev); ibm = torch.zeros(N_ITEMS, device=dev); gbm = torch.zeros(1, device=dev)
+        mloss = torch.zeros(1, dtype=torch.float64, device=dev)
+        for w in range(3):
+            ops.mf_pointwise_step_f32(Um, Vm, ubm, ibm, gbm, D, pos_u, indices, 1, N_ITEMS, 9, 0, 0.05, 0.0025, loss=mloss,
+                                      first=w * BATCH, count=BATCH)
+        torch.cuda.synchronize()
+        s0.record()
+        MREP = 5
+        for w in range(MREP):
+            ops.mf_pointwise_step_f32(Um, Vm, ubm, ibm, gbm, D, pos_u, indices, 1, N_ITEMS, 9, 0, 0.05, 0.0025, loss=mloss,
+                                      first=(3 + w) * BATCH, count=BATCH)
+        s1.record(); torch.cuda.synchronize()
+        mf_ms = s0.elapsed_time(s1) / MREP
+        mf_rate = {"metric": "mf2020_samples_per_sec", "value": BATCH / (mf_ms * 1e-3), "unit": "samples/s", "ms": mf_ms,
+                   "config": {"workload": f"MF2020 pointwise step, C2 tables, {BATCH} samples/launch (positives + m=1 uniform "
+                                          "negatives, fused sampling), fp32 Hogwild"},
+                   "roofline": {"bound": "hbm", "alg_bytes_per_sample": 2 * (2 * D * 4 + 2 * 4),
+                                "achieved": 2 * (2 * D * 4 + 2 * 4) * BATCH / (mf_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                "frac": 2 * (2 * D * 4 + 2 * 4) * BATCH / (mf_ms * 1e-3) / 1e9 / load_peaks()[0]},
+                   "finite": bool(torch.isfinite(Um).all().item() and torch.isfinite(gbm).all().item())}
+        del Um, Vm, pos_u
     finite = bool(torch.isfinite(U).all().item() and torch.isfinite(V).all().item())
     if not finite:
         raise RuntimeError("tables went non-finite during the benchmark: the numbers would be meaningless")
@@ -511,6 +540,8 @@ def main():
                                           "peak_source": "measured bf16_tflops (burst) from MEASURED_PEAKS.json; "
                                                          "`achieved` counts 2*d*I flop/user, `executed` the K padded for the folded bias"}},
     }
+    if mf_rate is not None:
+        out["mf2020"] = mf_rate
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(indptr.cpu().numpy(), indices.cpu().numpy())
     print(json.dumps(out))

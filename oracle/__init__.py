@@ -9,7 +9,8 @@ Parity pinning: the reference ships no tests or golden vectors, 
 ``oracle/gen_golden.py`` runs the reference's own ``custom_sampler.py`` /
 ``BPRMF_model.py`` (by file path, in the build container) and commits the outputs
 under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this restatement
-against them.  The TF-based variants (BPRMF_batch, NeuMF, MultiVAE) cannot be run
+against them; the MF2020 restatement (``mf2020_update_seq`` / ``mf2020_epoch_samples``) is pinned the same way
+against ``tests/golden/mf2020_*.npz`` (reference MF2020 sampler + model run).  The TF-based variants (BPRMF_batch, NeuMF, MultiVAE) cannot be run
 (tensorflow==2.3.2 is absent): their restatements in ``oracle/tf_models.py`` are
 "parity unpinned" and say so.
 """
