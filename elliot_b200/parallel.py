@@ -61,6 +61,31 @@ class ReplicatedTableSync:
             self._apply(t, p, d, scale)
 
 
+class GradAllReduce:
+    """Data-parallel dense weights (MultiVAE encoder/decoder, NeuMF MLP — SURVEY.md §8e): every rank holds the same
+    weights, computes gradients on its slice of the batch, and the gradients are AVERAGED with one all-reduce over
+    one flat buffer before the (identical) optimizer step.  `extra` (optional): small tensors summed along the way
+    (loss accumulators)."""
+
+    def __init__(self, flat, group=None, extra=None):
+        self.flat, self.group, self.extra = flat, group, extra
+
+    def sync(self):
+        if not dist.is_initialized():
+            return 1
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return 1
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)      # the division happens inside NCCL
+        else:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(world)
+        if self.extra is not None:
+            dist.all_reduce(self.extra, group=self.group)
+        return world
+
+
 class OverlappedTableSync:
     """Same reconciliation, one step late, so the all-reduce of step k overlaps the compute of step k+1
     (Hogwild tolerates the extra staleness; nothing is lost or double counted):

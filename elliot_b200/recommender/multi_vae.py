@@ -11,6 +11,7 @@ TensorFlow parity is UNPINNED (TF cannot run here); arithmetic is checked agains
 oracle/tf_models.py::multivae_forward_backward.
 """
 import math
+import os
 import pickle
 import random
 
@@ -46,12 +47,26 @@ class VariationalAutoEncoder:
                   "W3": glorot(H, L, L, H), "b3": torch.zeros(_pad4(H), device=self.device),
                   "W4": glorot(I, H, H, I), "b4": torch.zeros(_pad4(I), device=self.device)}
         z = lambda t: torch.zeros_like(t)
-        self.G = {k: z(v) for k, v in self.P.items()}
+        # gradients live in ONE flat buffer (views per parameter): data-parallel training all-reduces it in one call
+        self._gflat = torch.zeros(sum(v.numel() for v in self.P.values()), device=self.device)
+        self.G, off = {}, 0
+        for k, v in self.P.items():
+            self.G[k] = self._gflat[off:off + v.numel()].view_as(v); off += v.numel()
+        self.dp, self._salt = None, 0
         self.M = {k: z(v) for k, v in self.P.items()}
         self.V = {k: z(v) for k, v in self.P.items()}
         self.step = 0
         self._acc = torch.zeros(2, dtype=torch.float64, device=self.device)      # [kl_sum, nll_sum]
         self._refresh()
+
+    def enable_data_parallel(self, group=None):
+        """Replicated weights, batch split across the ranks of `group`, gradients averaged by one all-reduce
+        (SURVEY.md §8e).  Every rank must be constructed with the same seed (same initial weights); the dropout and
+        reparameterisation noise is salted with the rank so the slices draw independent noise."""
+        import torch.distributed as dist
+        from ..parallel import GradAllReduce
+        self.dp = GradAllReduce(self._gflat, group, extra=self._acc)
+        self._salt = 0x9E3779B1 * (dist.get_rank(group) if dist.is_initialized() else 0)
 
     def _refresh(self):
         """bf16 operand copies of the weights in both orientations (after every optimizer step)."""
@@ -66,20 +81,29 @@ class VariationalAutoEncoder:
         dev = self.device
         h1 = torch.empty((B, H), device=dev)
         ops.vae_embed_fwd(self.P["W1"], self.P["b1"], self.indptr, self.indices, rows, h1,
-                          self.drop if train else 0.0, self.seed * 7919 + step_id)
+                          self.drop if train else 0.0, self.seed * 7919 + step_id + self._salt)
         ml = ops.gemm_bf16_tn(ops.to_bf16(h1), self.W2b, B, 2 * L, H, bias=self.P["b2"])
         z = torch.empty((B, L), device=dev)
-        ops.vae_reparam_fwd(ml, L, z, self.seed, step_id, kl_sum)
+        ops.vae_reparam_fwd(ml, L, z, self.seed + self._salt, step_id, kl_sum)
         h2 = ops.gemm_bf16_tn(ops.to_bf16(z), self.W3b, B, H, L, bias=self.P["b3"], act=1)
         logits = ops.gemm_bf16_tn(ops.to_bf16(h2), self.W4b, B, I, H, bias=self.P["b4"])
         return h1, ml, z, h2, logits
 
     def train_step(self, rows, anneal):
         """rows: int32 device tensor of private user ids.  Returns the loss as a python float."""
-        B, H, L, I = rows.numel(), self.H, self.L, self.I
+        B, L = rows.numel(), self.L
         self.step += 1
-        sid = self.step
         self._acc.zero_()
+        self.compute_grads(rows, anneal, self.step)
+        world = self.dp.sync() if self.dp is not None else 1     # data parallel: average grads, sum the loss terms
+        self.apply_grads()
+        kl_sum, nll_sum = self._acc.tolist()
+        Bg = B * world                                           # equal slices (the caller splits evenly, +-1 row)
+        return nll_sum / Bg + anneal * (-0.5 * kl_sum / (Bg * L))
+
+    def compute_grads(self, rows, anneal, sid):
+        """Forward + backward of one batch: gradients into self.G (views of one flat buffer), loss terms into _acc."""
+        B, H, L, I = rows.numel(), self.H, self.L, self.I
         h1, ml, z, h2, logits = self._forward(rows, sid, self._acc[0:1])
         ops.vae_softmax(logits, self.indptr, self.indices, rows, nll_sum=self._acc[1:2], write_grad=True)
         dlogits = logits                                                       # in place
@@ -93,18 +117,19 @@ class VariationalAutoEncoder:
         ops.colsum(dpre2, G["b3"])
         dz = ops.gemm_bf16_tn(ops.to_bf16(dpre2), self.W3t, B, L, H)
         dml = torch.empty((B, 2 * L), device=self.device)
-        ops.vae_reparam_bwd(ml, L, dz, dml, self.seed, sid, float(anneal))
+        ops.vae_reparam_bwd(ml, L, dz, dml, self.seed + self._salt, sid, float(anneal))
         ops.gemm_bf16_tn(ops.to_bf16(dml, transpose=True), ops.to_bf16(h1, transpose=True), 2 * L, H, B, out=G["W2"])
         ops.colsum(dml, G["b2"])
         dh1 = ops.gemm_bf16_tn(ops.to_bf16(dml), self.W2t, B, H, 2 * L)
         dpre1 = ops.tanh_bwd(dh1, h1)
         ops.colsum(dpre1, G["b1"])
-        ops.vae_embed_bwd(G["W1"], self.indptr, self.indices, rows, dpre1, self.drop, self.seed * 7919 + sid)
+        ops.vae_embed_bwd(G["W1"], self.indptr, self.indices, rows, dpre1, self.drop, self.seed * 7919 + sid + self._salt)
+
+    def apply_grads(self):
+        """Keras Adam on every parameter (clears the gradients), then refresh the bf16 operand copies."""
         for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"):
-            ops.adam_dense_f32(self.P[k], self.M[k], self.V[k], G[k], self.lr, self.step)
+            ops.adam_dense_f32(self.P[k], self.M[k], self.V[k], self.G[k], self.lr, self.step)
         self._refresh()
-        kl_sum, nll_sum = self._acc.tolist()
-        return nll_sum / B + anneal * (-0.5 * kl_sum / (B * L))
 
     def predict_topk(self, rows, k, mask_indptr, mask_indices):
         """log_softmax(decoder(z)) with the train mask -> top-k (multi_vae_model.py:144-159); note the
@@ -160,13 +185,22 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
         self._dropout_rate = 1. - self._dropout_rate
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.MultiVAE needs a CUDA device (there is no CPU fallback)")
-        self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
+        # b200_dp: true (under torchrun) -> data parallel: replicated weights, every batch split across the ranks,
+        # gradients averaged by one all-reduce per step; each rank drives the GPU of its LOCAL_RANK
+        self._dp = bool(getattr(self._params, "b200_dp", False))
+        default_dev = f"cuda:{os.environ.get('LOCAL_RANK', '0')}" if self._dp else "cuda:0"
+        self._device = torch.device(getattr(self._params, "b200_device", default_dev))
         self._indptr, _, self._sorted_idx = self._data.train_csr(self._device)
         self._model = VariationalAutoEncoder(self._num_items, self._intermediate_dim, self._latent_dim, self._learning_rate,
                                              self._dropout_rate, self._lambda, self._seed, self._indptr, self._sorted_idx,
                                              self._device)
         self._total_anneal_steps = 200000
         self._anneal_cap = 0.2
+        if self._dp:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise Exception("b200_dp needs an initialised torch.distributed process group (launch with torchrun)")
+            self._model.enable_data_parallel()
 
     @property
     def name(self):
@@ -182,6 +216,11 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
             order = torch.tensor(order, dtype=torch.int32, device=self._device)
             for s in range(0, self._num_users, self._batch_size):
                 rows = order[s:s + self._batch_size].contiguous()
+                if self._dp:                                     # this rank's slice of the batch (sizes differ by <= 1)
+                    import torch.distributed as dist
+                    from ..parallel import shard_range
+                    lo, hi = shard_range(rows.numel(), dist.get_rank(), dist.get_world_size())
+                    rows = rows[lo:hi].contiguous()
                 anneal = min(self._anneal_cap, 1. * self._update_count / self._total_anneal_steps) \
                     if self._total_anneal_steps > 0 else self._anneal_cap
                 loss += self._model.train_step(rows, anneal)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from elliot_b200.parallel import (OverlappedTableSync, ReplicatedTableSync, ShardedTable, gather_topk, owner_of,
+from elliot_b200.parallel import (GradAllReduce, OverlappedTableSync, ReplicatedTableSync, ShardedTable, gather_topk, owner_of,
                                   shard_range)
 
 
@@ -106,6 +106,12 @@ def _worker(rank, world, init_file, out_dir):
         rid = torch.tensor([12, 0, 5, 5, 7, r, 11 - r])
         want.index_add_(0, rid, torch.ones(len(rid), 4) * (r + 1))
     ok = ok and torch.equal(st.local, want[lo:hi])
+    # data-parallel dense grads: one flat buffer averaged, loss accumulators summed
+    gflat = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    acc = torch.tensor([1.0 + rank, 10.0], dtype=torch.float64)
+    w = GradAllReduce(gflat, extra=acc).sync()
+    ok = ok and w == world and torch.allclose(gflat, torch.arange(6, dtype=torch.float32) * sum(r + 1 for r in range(world)) / world) \
+        and torch.equal(acc, torch.tensor([sum(1.0 + r for r in range(world)), 10.0 * world], dtype=torch.float64))
     torch.save({"ok": ok, "V": V}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
