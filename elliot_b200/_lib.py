@@ -69,6 +69,8 @@ SIGNATURES = {
                                      c_void, c_void, c_void, c_void]),
     "eb_table_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_table_apply_delta_f32": (c_int, [c_void, c_void, c_void, c_i64, c_f32, c_void]),
+    "eb_vae_step_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int]),
+    "eb_vae_train_step": (c_int, [c_void, c_void, c_int, c_f32, c_u64, c_u64, c_u64, c_f32, c_f32, c_void, c_void, c_size, c_int, c_void]),
     "eb_mf_pointwise_exact_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
                                   c_f64, c_f64, c_i64, c_void, c_void]),
     "eb_mf_pointwise_step_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_i64, c_int, c_i32,

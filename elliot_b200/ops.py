@@ -267,6 +267,52 @@ def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
     return out
 
 
+# ---------------------------------------------------------------- MultiVAE: whole step in one call (vae_step.cu)
+class _VaeModelStruct(ctypes.Structure):
+    _fields_ = ([("n_items", ctypes.c_int), ("H", ctypes.c_int), ("L", ctypes.c_int), ("reserved", ctypes.c_int)]
+                + [(f"{pre}{k}", ctypes.c_void_p) for pre in ("", "g", "m", "v")
+                   for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4")]
+                + [(k, ctypes.c_void_p) for k in ("W2b", "W3b", "W4b", "W2t", "W3t", "W4t", "indptr", "indices")])
+
+
+def vae_model_struct(n_items, H, L, P, G, M, V, bf16_copies, indptr, indices):
+    """eb_vae_model over existing device tensors (which must outlive the struct and never be reallocated)."""
+    _need_cuda(indptr, indices, *P.values(), *G.values(), *M.values(), *V.values(), *bf16_copies)
+    st = _VaeModelStruct()
+    st.n_items, st.H, st.L, st.reserved = n_items, H, L, 0
+    for pre, d in (("", P), ("g", G), ("m", M), ("v", V)):
+        for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"):
+            assert d[k].dtype == torch.float32 and d[k].is_contiguous()
+            setattr(st, pre + k, d[k].data_ptr())
+    for name, t in zip(("W2b", "W3b", "W4b", "W2t", "W3t", "W4t"), bf16_copies):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        setattr(st, name, t.data_ptr())
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+    st.indptr, st.indices = indptr.data_ptr(), indices.data_ptr()
+    st._keep = (P, G, M, V, bf16_copies, indptr, indices)
+    return st
+
+
+_vae_ws = {}
+
+
+def vae_train_step(model, n_items, H, L, rows, drop_rate, noise_seed, drop_seed, step, anneal, lr, acc, phase=3):
+    """eb_vae_train_step: phase bit 0 = forward+backward into the gradient buffers, bit 1 = Adam + operand refresh."""
+    _need_cuda(acc, rows)
+    dev = acc.device
+    B = rows.numel() if rows is not None else 0
+    ws = None
+    if phase & 1:
+        _chk_idx(rows)
+        need = lib().eb_vae_step_workspace_bytes(n_items, H, L, B)
+        ws = _vae_ws.get(dev)
+        if ws is None or ws.numel() < need:
+            ws = _vae_ws[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().eb_vae_train_step(ctypes.byref(model), _ptr(rows), B, drop_rate, noise_seed, drop_seed, step, anneal, lr,
+                                      _ptr(acc), _ptr(ws), ws.numel() if ws is not None else 0, phase, _stream(acc)))
+
+
 # ---------------------------------------------------------------- MultiVAE pieces (vae.cu)
 def vae_embed_fwd(W1, b1, indptr, indices, rows, h1, drop_rate=0.0, seed=0):
     _need_cuda(W1, b1, indptr, indices, rows, h1)

@@ -53,6 +53,7 @@ class VariationalAutoEncoder:
         for k, v in self.P.items():
             self.G[k] = self._gflat[off:off + v.numel()].view_as(v); off += v.numel()
         self.dp, self._salt = None, 0
+        self.native = True                                     # one native call per step phase (csrc/vae_step.cu)
         self.M = {k: z(v) for k, v in self.P.items()}
         self.V = {k: z(v) for k, v in self.P.items()}
         self.step = 0
@@ -69,11 +70,24 @@ class VariationalAutoEncoder:
         self._salt = 0x9E3779B1 * (dist.get_rank(group) if dist.is_initialized() else 0)
 
     def _refresh(self):
-        """bf16 operand copies of the weights in both orientations (after every optimizer step)."""
+        """bf16 operand copies of the weights in both orientations (after every optimizer step); the buffers are
+        allocated once so the native step can keep their addresses."""
         P = self.P
-        self.W2b, self.W3b, self.W4b = ops.to_bf16(P["W2"]), ops.to_bf16(P["W3"]), ops.to_bf16(P["W4"])
-        self.W2t, self.W3t, self.W4t = (ops.to_bf16(P["W2"], transpose=True), ops.to_bf16(P["W3"], transpose=True),
-                                        ops.to_bf16(P["W4"], transpose=True))
+        if not hasattr(self, "W2b"):
+            self.W2b = self.W3b = self.W4b = self.W2t = self.W3t = self.W4t = None
+        self.W2b, self.W3b, self.W4b = (ops.to_bf16(P["W2"], out=self.W2b), ops.to_bf16(P["W3"], out=self.W3b),
+                                        ops.to_bf16(P["W4"], out=self.W4b))
+        self.W2t, self.W3t, self.W4t = (ops.to_bf16(P["W2"], transpose=True, out=self.W2t),
+                                        ops.to_bf16(P["W3"], transpose=True, out=self.W3t),
+                                        ops.to_bf16(P["W4"], transpose=True, out=self.W4t))
+
+    def _native_model(self):
+        """The eb_vae_model struct (include/elliot_b200.h) over this model's tensors."""
+        if getattr(self, "_cmodel", None) is None:
+            self._cmodel = ops.vae_model_struct(self.I, self.H, self.L, self.P, self.G, self.M, self.V,
+                                                (self.W2b, self.W3b, self.W4b, self.W2t, self.W3t, self.W4t),
+                                                self.indptr, self.indices)
+        return self._cmodel
 
     # ---- forward up to the logits (multi_vae_model.py:56-64,80-83,114-123)
     def _forward(self, rows, step_id, kl_sum=None, train=True):
@@ -102,7 +116,14 @@ class VariationalAutoEncoder:
         return nll_sum / Bg + anneal * (-0.5 * kl_sum / (Bg * L))
 
     def compute_grads(self, rows, anneal, sid):
-        """Forward + backward of one batch: gradients into self.G (views of one flat buffer), loss terms into _acc."""
+        """Forward + backward of one batch: gradients into self.G (views of one flat buffer), loss terms into _acc.
+        native (default): one C-ABI call issues all ~33 kernels (eb_vae_train_step phase 1); the launch-by-launch
+        Python sequence below is the same kernels in the same order and is kept as the readable specification
+        (tests/test_gpu_multivae.py checks the two against each other)."""
+        if self.native:
+            ops.vae_train_step(self._native_model(), self.I, self.H, self.L, rows, self.drop, self.seed + self._salt,
+                               self.seed * 7919 + sid + self._salt, sid, float(anneal), self.lr, self._acc, phase=1)
+            return
         B, H, L, I = rows.numel(), self.H, self.L, self.I
         h1, ml, z, h2, logits = self._forward(rows, sid, self._acc[0:1])
         ops.vae_softmax(logits, self.indptr, self.indices, rows, nll_sum=self._acc[1:2], write_grad=True)
@@ -127,6 +148,10 @@ class VariationalAutoEncoder:
 
     def apply_grads(self):
         """Keras Adam on every parameter (clears the gradients), then refresh the bf16 operand copies."""
+        if self.native:
+            ops.vae_train_step(self._native_model(), self.I, self.H, self.L, None, self.drop, 0, 0, self.step, 0.0, self.lr,
+                               self._acc, phase=2)
+            return
         for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"):
             ops.adam_dense_f32(self.P[k], self.M[k], self.V[k], self.G[k], self.lr, self.step)
         self._refresh()

@@ -177,6 +177,28 @@ int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr
                    const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *stream);
 int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
 int eb_colsum(const float *src, int rows, int cols, int64_t ld, float *out, void *stream);
+/* One whole MultiVAE training step as ONE native call: the same kernels as the entry points above, issued back to back
+ * from C++ (the step is ~47 launches and interpreter-bound when driven from Python).  Replaces
+ * VariationalAutoEncoder.train_step (multi_vae_model.py:125-142).  Layouts: W1 [I][H] fp32; W2 [2L][H], W3 [H][L],
+ * W4 [I][H] fp32 ([out][in]); biases padded to multiples of 4; g* gradients, m* / v* Adam moments, same shapes;
+ * W?b / W?t: bf16 operand copies ([out][pad8(in)] and transposed [in][pad8(out)]), refreshed by phase bit 1.
+ * phase: bit 0 = forward + backward (gradients into g*, acc[0] += KL sum term, acc[1] += NLL sum);
+ *        bit 1 = Adam (lr_t = lr sqrt(1-b2^step)/(1-b1^step), clears g*) + operand refresh.
+ * A data-parallel caller runs phase 1, all-reduces the gradients, then phase 2. */
+typedef struct eb_vae_model {
+    int n_items, H, L, reserved;
+    float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;
+    float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3, *gW4, *gb4;
+    float *mW1, *mb1, *mW2, *mb2, *mW3, *mb3, *mW4, *mb4;
+    float *vW1, *vb1, *vW2, *vb2, *vW3, *vb3, *vW4, *vb4;
+    void *W2b, *W3b, *W4b, *W2t, *W3t, *W4t;
+    const int64_t *indptr;
+    const int32_t *indices;
+} eb_vae_model;
+size_t eb_vae_step_workspace_bytes(int n_items, int H, int L, int B);
+int eb_vae_train_step(const eb_vae_model *m, const int32_t *rows, int B, float drop_rate, uint64_t noise_seed,
+                      uint64_t drop_seed, uint64_t step, float anneal, float lr, double *acc, void *workspace,
+                      size_t workspace_bytes, int phase, void *stream);
 /* masked top-k over an existing dense score block (scores are overwritten); out_val = score + shift[row] */
 int eb_dense_topk_f32(float *scores, int64_t ld, int n_rows, int n_items, const int64_t *mask_indptr,
                       const int32_t *mask_indices, const int32_t *rows, const float *shift, int k, int32_t *out_idx,

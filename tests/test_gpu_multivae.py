@@ -94,3 +94,21 @@ def test_multivae_yaml_trains(tmp_path):
     r0 = run_experiment(cfg(1, 0.0))
     r1 = run_experiment(cfg(60, 0.003))
     assert r1[0]["test_results"][10]["nDCG"] > 1.5 * r0[0]["test_results"][10]["nDCG"] + 0.02
+
+
+@pytest.mark.parametrize("nu,ni,H,L,B,drop", [(300, 1000, 64, 24, 160, 0.0), (500, 3001, 600, 200, 77, 0.4)])
+def test_native_step_equals_launch_by_launch_sequence(nu, ni, H, L, B, drop):
+    """eb_vae_train_step (one C-ABI call per phase) issues the same kernels in the same order as the Python
+    sequence: same loss, same weights after a few steps (only the fp32 atomics of the sparse first layer reorder)."""
+    _, indptr, indices = _csr(nu, ni, 30, 3)
+    a = VariationalAutoEncoder(ni, H, L, 1e-3, drop, 0.01, 7, indptr, indices, DEV)
+    b = VariationalAutoEncoder(ni, H, L, 1e-3, drop, 0.01, 7, indptr, indices, DEV)
+    b.native = False
+    rs = np.random.RandomState(0)
+    for step in range(4):
+        rows = torch.from_numpy(rs.choice(nu, B, replace=False).astype(np.int32)).to(DEV)
+        la, lb = a.train_step(rows, 0.05 * step), b.train_step(rows, 0.05 * step)
+        assert abs(la - lb) < 1e-6 * abs(lb) + 1e-9
+    for k in a.P:
+        assert (a.P[k] - b.P[k]).abs().max().item() < 2e-6, k
+    assert torch.equal(a.W4b, ops.to_bf16(a.P["W4"])) and torch.equal(a.W3t, ops.to_bf16(a.P["W3"], transpose=True))
