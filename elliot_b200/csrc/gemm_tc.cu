@@ -73,6 +73,7 @@ struct GemmParams {
     int M, N, K;
     int act;             // 0 none, 1 tanh, 2 relu
     float alpha;         // C = alpha * (A B^T) + bias, then activation
+    int splits;          // split-K factor: > 1 -> each work item covers a K range and ADDS into a zeroed C (no bias/act)
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -87,8 +88,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * G_STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + G_BM - 1) / G_BM, tiles_n = (p.N + G_BN - 1) / G_BN;
-    const int n_tiles = tiles_m * tiles_n;
-    const int k_blocks = (p.K + G_BK - 1) / G_BK;
+    const int k_blocks_all = (p.K + G_BK - 1) / G_BK;
+    const int kb_per = (k_blocks_all + p.splits - 1) / p.splits;     // k-blocks per split (the last may be shorter)
+    const int n_tiles = tiles_m * tiles_n * p.splits;               // work items: (tile, split)
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 
     if (threadIdx.x == 0) {
         if (g_smem_u32(sm) & 1023u) __trap();
@@ -108,9 +112,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < n_tiles; work += gridDim.x) {
+                const int tile = work / p.splits, split = work % p.splits;
                 const int tm = tile / tiles_n, tn = tile % tiles_n;
-                for (int kb = 0; kb < k_blocks; kb++) {
+                const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, k_blocks_all);
+                for (int kb = kb0; kb < kb1; kb++) {
                     g_mbar_wait(EMPTY(s), ph ^ 1);
                     g_mbar_expect_tx(FULL(s), G_STAGE_BYTES);
                     const uint32_t a_dst = g_smem_u32(sm + s * G_STAGE_BYTES), b_dst = a_dst + G_BM * G_BK * 2;
@@ -125,18 +131,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // instruction descriptor: fp32 accum, bf16 A/B, K-major both, N=128, M=128
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
             int s = 0; uint32_t ph = 0; uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            for (int work = blockIdx.x; work < n_tiles; work += gridDim.x, it++) {
+                const int split = work % p.splits;
+                const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, k_blocks_all);
                 const int acc = it & 1;
                 g_mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G_BN);
-                for (int kb = 0; kb < k_blocks; kb++) {
+                for (int kb = kb0; kb < kb1; kb++) {
                     g_mbar_wait(FULL(s), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = g_smem_u32(sm + s * G_STAGE_BYTES), b_addr = a_addr + G_BM * G_BK * 2;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        g_umma(d_tmem, g_desc_sw128(a_addr + k * 32), g_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        g_umma(d_tmem, g_desc_sw128(a_addr + k * 32), g_desc_sw128(b_addr + k * 32), idesc, ((kb - kb0) | k) != 0);
                     g_commit(EMPTY(s));
                     if (++s == G_STAGES) { s = 0; ph ^= 1; }
                 }
@@ -146,8 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const int quad = warp & 3;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        for (int work = blockIdx.x; work < n_tiles; work += gridDim.x, it++) {
+            const int tile = work / p.splits, split = work % p.splits;
             const int tm = tile / tiles_n, tn = tile % tiles_n;
+            const bool empty = split * kb_per >= k_blocks_all;          // trailing split without k-blocks: nothing was issued
             const int acc = it & 1;
             g_mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -168,17 +178,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     : "r"(taddr + (uint32_t)c0)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < p.M) {
+                if (row < p.M && !empty) {
                     float *crow = p.C + (int64_t)row * p.ldc;
                     const int col0 = tn * G_BN + c0;
+                    if (vec_ok && col0 + 32 <= p.N) {
+                        // each lane owns 32 consecutive floats of its row: 128-bit stores (8 per chunk) instead of 32 scalar ones
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int col = col0 + c;
-                        if (col < p.N) {
-                            float x = p.alpha * __uint_as_float(r[c]) + (p.bias ? __ldg(p.bias + col) : 0.f);
-                            if (p.act == 1) x = tanhf(x);
-                            else if (p.act == 2) x = fmaxf(x, 0.f);
-                            crow[col] = x;
+                        for (int c = 0; c < 32; c += 4) {
+                            float4 o = make_float4(p.alpha * __uint_as_float(r[c]), p.alpha * __uint_as_float(r[c + 1]),
+                                                   p.alpha * __uint_as_float(r[c + 2]), p.alpha * __uint_as_float(r[c + 3]));
+                            if (p.splits > 1) {
+                                red_add_v4(crow + col0 + c, o);
+                            } else {
+                                if (p.bias) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + c));
+                                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                                }
+                                if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+                                else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                *reinterpret_cast<float4 *>(crow + col0 + c) = o;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const int col = col0 + c;
+                            if (col < p.N) {
+                                float x = p.alpha * __uint_as_float(r[c]);
+                                if (p.splits > 1) { red_add_f32(crow + col, x); continue; }
+                                x += p.bias ? __ldg(p.bias + col) : 0.f;
+                                if (p.act == 1) x = tanhf(x);
+                                else if (p.act == 2) x = fmaxf(x, 0.f);
+                                crow[col] = x;
+                            }
                         }
                     }
                 }
@@ -274,9 +306,25 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
     CUtensorMap ma, mb;
     if (int rc = g_make_map(&ma, A_bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM)) return rc;
     if (int rc = g_make_map(&mb, B_bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, G_BN)) return rc;
-    GemmParams p{C, ldc, bias, M, N, K, act, alpha};
+    const int n_out_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+    const int k_blocks = (K + G_BK - 1) / G_BK;
+    // split-K: few output tiles with a long K (dh2 = dlogits . W4: 20 tiles, K = 26 744) leave most SMs idle and each
+    // busy CTA load-latency bound; split the K range over the idle SMs and add the partial tiles into a zeroed C
+    int splits = 1;
+    if (!bias && act == 0 && n_out_tiles * 2 <= sm_count() && k_blocks >= 16) {
+        splits = sm_count() / n_out_tiles;
+        if (splits > k_blocks / 8) splits = k_blocks / 8;           // at least 8 k-blocks per work item
+        if (splits < 1) splits = 1;
+        const int per = (k_blocks + splits - 1) / splits;
+        splits = (k_blocks + per - 1) / per;                         // no empty trailing splits
+    }
+    GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits};
     EB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-    const int n_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+    if (splits > 1) {
+        if (ldc == N) EB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream));
+        else EB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, (cudaStream_t)stream));
+    }
+    const int n_tiles = n_out_tiles * splits;
     int grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
     gemm_tc_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, p);
