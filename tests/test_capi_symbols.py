@@ -56,3 +56,19 @@ def test_compute_call_fails_loudly_without_cuda():
     U = torch.zeros((4, 16)); b = torch.zeros(4); t = torch.zeros(4, dtype=torch.int32)
     with pytest.raises(RuntimeError):
         ops.bpr_step_f32(U, U, b, 10, t, t, t, 0.05, 0, 0, 0, 0)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/elliot_b200.h must compile as C99 (no C++ / torch / CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/elliot_b200.h"\nint main(void) { return eb_version() < 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
