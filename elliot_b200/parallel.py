@@ -212,11 +212,15 @@ class ShardedTable:
         self._plan = (order, sc, rc, local_ids)
         return rows_in[inv]
 
-    def push(self, deltas):
-        """deltas[t] is added to global row ids[t] of the last fetch (duplicates accumulate)."""
+    def push(self, deltas, target=None):
+        """deltas[t] is added to global row ids[t] of the last fetch (duplicates accumulate).  target (optional): a
+        tensor partitioned like the table (e.g. this rank's dense GRADIENT shard for an Adam-trained table) that
+        receives the rows instead of the table itself."""
         order, sc, rc, local_ids = self._plan
         back = self._exchange(deltas[order].contiguous(), sc, rc)
-        self._scatter(self.local, local_ids, back)
+        dst = self.local if target is None else target
+        assert dst.shape[0] == self.hi - self.lo
+        self._scatter(dst, local_ids, back)
 
 
 def sharded_bpr_step(U_local, items: "ShardedTable", tu_local, ti, tj, hyper, bias_col=-1, loss=None, step_fn=None):

@@ -106,6 +106,13 @@ def _worker(rank, world, init_file, out_dir):
         rid = torch.tensor([12, 0, 5, 5, 7, r, 11 - r])
         want.index_add_(0, rid, torch.ones(len(rid), 4) * (r + 1))
     ok = ok and torch.equal(st.local, want[lo:hi])
+    # push into a separate target (the dense gradient shard of an Adam-trained table): the table itself stays put
+    before = st.local.clone()
+    gshard = torch.zeros_like(st.local)
+    st.fetch(ids)
+    st.push(torch.ones(len(ids), 4) * (rank + 1), target=gshard)
+    dist.barrier()
+    ok = ok and torch.equal(st.local, before) and torch.equal(gshard, (want - full)[lo:hi])
     # data-parallel dense grads: one flat buffer averaged, loss accumulators summed
     gflat = torch.arange(6, dtype=torch.float32) * (rank + 1)
     acc = torch.tensor([1.0 + rank, 10.0], dtype=torch.float64)
