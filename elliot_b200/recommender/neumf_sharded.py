@@ -1,9 +1,10 @@
 """NeuMF with row-sharded embedding tables (BASELINE configs[3]: 10 M users x 1 M items over 4 GPUs).
 
-STATUS: written at the end of round 1 after the round's GPU budget was spent — composed only of kernels that are
-tested on the B200 (`eb_neumf_*`, `eb_gemm_bf16_tn`, `eb_gather/scatter_add_rows_f32`, `eb_adam_dense_f32`) and of
-`parallel.ShardedTable` / `GradAllReduce` (gloo-tested), but NOT yet run on GPUs itself; `tools/neumf_sharded_check.py`
-is the 2-GPU check to run first next round.  Nothing imports this module by default.
+STATUS (end of round 1): composed only of kernels that are tested on the B200 (`eb_neumf_*`, `eb_gemm_bf16_tn`,
+`eb_gather/scatter_add_rows_f32`, `eb_adam_dense_f32`) and of `parallel.ShardedTable` / `GradAllReduce` (gloo-tested).
+Run on one B200 at world = 1 it tracks the ordinary model to 1e-8 over 3 steps (`tools/neumf_sharded_w1.py`,
+profiles/r1f_neumf_sharded_w1.json); the multi-GPU run (`tools/neumf_sharded_check.py`) is pending — the round's GPU
+budget was spent.  Nothing imports this module by default.
 
 Layout: users are block-partitioned over the ranks (`shard_range`), each rank holds the MF and MLP rows of its own
 users and samples only for them, so user rows never move.  The two item tables are stored side by side in ONE
