@@ -100,3 +100,25 @@ def test_neumf_yaml_trains(tmp_path):
     r0 = run_experiment(cfg(1, 0.0))
     r1 = run_experiment(cfg(30, 0.003))
     assert r1[0]["test_results"][10]["nDCG"] > 1.5 * r0[0]["test_results"][10]["nDCG"] + 0.02
+
+
+def test_sharded_model_at_world_1_tracks_the_ordinary_model():
+    """recommender/neumf_sharded.py (row-sharded item tables) with no process group: every all-to-all
+    degenerates to a copy, so the step must equal the ordinary model's (same kernels on fetched row copies)."""
+    from elliot_b200.recommender.neumf import NeuralMatrixFactorizationModel
+    from elliot_b200.recommender.neumf_sharded import ShardedNeuMFModel
+    dev = torch.device(DEV)
+    NU, NI, F, B = 3000, 2000, 32, 2048
+    sh = ShardedNeuMFModel(NU, NI, F, 1e-3, 42, dev); ref = NeuralMatrixFactorizationModel(NU, NI, F, 1e-3, 42, dev)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    for s in range(3):
+        u = torch.randint(0, NU, (B,), device=dev, generator=g, dtype=torch.int32)
+        it = torch.randint(0, NI, (B,), device=dev, generator=g, dtype=torch.int32)
+        y = (torch.rand(B, device=dev, generator=g) < 0.3).float()
+        la, lb = sh.train_step((u, it, y)).item(), ref.train_step((u, it, y)).item()
+        assert abs(la - lb) < 1e-6 * abs(lb)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(sh.P["U_mf"], ref.P["U_mf"]) < 1e-5 and rel(sh.P["U_mlp"], ref.P["U_mlp"]) < 1e-5
+    assert rel(sh.P["I"][:, :F], ref.P["I_mf"]) < 1e-5 and rel(sh.P["I"][:, F:], ref.P["I_mlp"]) < 1e-5
+    for k in ("W1", "W2", "W3", "wp"):
+        assert rel(sh.P[k], ref.P[k]) < 1e-5, k
