@@ -220,7 +220,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+    # stdout carries exactly one JSON line: NCCL stays silent unless the caller asks for debug output (NCCL_DEBUG), and
+    # then that output goes to stderr (with NCCL_DEBUG=WARN/INFO NCCL prints its version banner on stdout otherwise)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from elliot_b200 import ops
