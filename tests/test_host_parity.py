@@ -138,3 +138,36 @@ def test_mf2020_sampler_replays_reference_epochs(case):
     assert np.array_equal(np.stack([smp.pos_u, smp.pos_i], 1), g["positives"])
     for ep in range(int(g["epochs"])):
         assert np.array_equal(smp.epoch(), g[f"samples_ep{ep}"])
+
+
+def test_device_evaluator_tables_match_per_user_loops(golden):
+    """Evaluator._device_set (inputs of eb_eval_topk_f64): item-sorted relevant rows, gains aligned with them, IDCG@k
+    per user — checked on the CPU against the straightforward per-user computation for every cutoff."""
+    import math
+    import torch
+    g = golden
+    data = DataSet(_config(int(g["k"])), _frames(g))
+    ev = Evaluator(data, SimpleNamespace(meta=SimpleNamespace()))
+    indptr, idx, gain = ev._sets["test"]
+    for k in (1, 3, int(g["k"])):
+        ip, items, gains, idcg, disc = (t.numpy() for t in ev._device_set("test", k, torch.device("cpu")))
+        assert np.array_equal(ip, indptr) and len(disc) == k
+        assert np.allclose(disc, [math.log(2) / math.log(r + 2) for r in range(k)], rtol=0, atol=0)
+        for u in range(data.num_users):
+            lo, hi = indptr[u], indptr[u + 1]
+            order = np.argsort(idx[lo:hi], kind="stable")
+            assert np.array_equal(items[lo:hi], idx[lo:hi][order]) and np.array_equal(gains[lo:hi], gain[lo:hi][order])
+            ideal = np.sort(gain[lo:hi])[::-1][:k]
+            assert abs(idcg[u] - float((ideal * disc[:len(ideal)]).sum())) < 1e-12
+
+
+def test_shard_range_and_owner_of_agree():
+    from elliot_b200.parallel import owner_of, shard_range
+    for n in (0, 1, 7, 64, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
+            for row in range(n):
+                r = owner_of(row, n, world)
+                assert edges[r][0] <= row < edges[r][1]
