@@ -1,6 +1,10 @@
 """Torch-tensor wrappers over the C ABI.  Torch is plumbing only (device memory, streams);
 all arithmetic happens in elliot_b200/csrc/*.cu.  Every op raises if its tensors are not on a
 CUDA device — there is no CPU path.
+
+Streams: every op launches on torch's CURRENT stream of the tensors' device.  The C ABI never allocates, so a few
+wrappers keep a grow-only scratch buffer per device (scoring, evaluation, the native MultiVAE step, the MF2020
+global-bias accumulator): those ops must not run concurrently on two streams of the same device from one process.
 """
 import ctypes
 
