@@ -56,6 +56,8 @@ SIGNATURES = {
     "eb_neumf_gather": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void]),
     "eb_neumf_head": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_void, c_void, c_i64, c_void, c_void, c_void, c_void,
                               c_void, c_void, c_void]),
+    "eb_neumf_head_norm": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void,
+                                   c_void, c_void, c_void, c_void]),
     "eb_relu_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_neumf_scatter": (c_int, [c_void, c_void, c_int, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_void,
                                  c_void, c_void, c_void]),
@@ -80,6 +82,22 @@ SIGNATURES = {
                          c_void, c_size, c_void]),
     "eb_partition_streams_create": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(c_int)]),
     "eb_table_apply_delta_late_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_void]),
+    "eb_peer_alloc": (c_int, [c_size, ctypes.POINTER(ctypes.c_void_p)]),
+    "eb_peer_free": (c_int, [c_void]),
+    "eb_peer_export": (c_int, [c_void, c_void]),
+    "eb_peer_open": (c_int, [c_void, ctypes.POINTER(ctypes.c_void_p)]),
+    "eb_peer_close": (c_int, [c_void]),
+    "eb_bpr_step_peer_f32": (c_int, [c_void, c_void, c_void, c_int, c_i32, c_int, c_int, c_i32, c_void, c_void, c_void, c_i64,
+                                     c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_int, c_void]),
+    "eb_bpr_step_sampled_peer_f32": (c_int, [c_void, c_void, c_void, c_int, c_i32, c_int, c_int, c_i32, c_i32, c_void, c_void,
+                                             c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void,
+                                             c_void, c_int, c_void]),
+    "eb_table_reconcile_peer_f32": (c_int, [c_void, c_int, c_void, c_i64, c_f32, c_int, c_void]),
+    "eb_neumf_gather_peer": (c_int, [c_void, c_void, c_i64, c_void, c_int, c_i32, c_i64, c_int, c_void, c_void, c_i64, c_void,
+                                     c_i64, c_void, c_i64, c_void]),
+    "eb_neumf_scatter_peer": (c_int, [c_void, c_i64, c_void, c_void, c_int, c_i32, c_i64, c_int, c_void, c_void, c_i64, c_void,
+                                      c_i64, c_void, c_i64, c_void, c_void, c_void]),
+    "eb_gather_rows_peer_f32": (c_int, [c_void, c_int, c_i32, c_i64, c_void, c_i64, c_int, c_void, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),
     "eb_score_topk_tc_f32": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_i32, c_i64, c_int,
                                      c_void, c_void, c_void, c_void, c_size, c_void, c_void]),

@@ -33,7 +33,20 @@ struct HogwildParams {
     const int32_t *indices;
     uint64_t seed, first;
     int32_t *out_u, *out_i, *out_j;
+    // PEER mode (item table row-sharded over the GPUs of one NVSwitch box): shard s holds item rows
+    // [s*shard_rows, (s+1)*shard_rows) at Vp[s] / bp[s] — local memory for this rank's shard, peer-mapped memory
+    // (cudaIpcOpenMemHandle, peer.cu) for the others; loads and vector atomics go straight over NVLink.
+    float *Vp[EB_MAX_PEERS], *bp[EB_MAX_PEERS];
+    uint32_t shard_rows, shard_magic;          // magic = floor(2^32 / shard_rows)
 };
+
+// owner shard and row inside it (one multiply-high and one correction instead of an integer division)
+__device__ __forceinline__ void shard_of(const HogwildParams &p, int i, int &owner, int &local) {
+    uint32_t o = __umulhi((uint32_t)i, p.shard_magic);
+    uint32_t r = (uint32_t)i - o * p.shard_rows;
+    if (r >= p.shard_rows) { o++; r -= p.shard_rows; }
+    owner = (int)o; local = (int)r;
+}
 
 
 // u uniform over users, i uniform over the user's train items, j uniform over the
@@ -71,7 +84,7 @@ struct Rows {
     float bi, bj;
 };
 
-template <int DP, bool SAMPLE, bool ATOMIC>
+template <int DP, bool SAMPLE, bool ATOMIC, bool PEER>
 __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p) {
     constexpr int NV = DP / 4;                 // float4 per row
     constexpr int G = NV >= 32 ? 32 : NV;      // lanes per triple
@@ -84,19 +97,31 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
     const int64_t ld = p.ld;
     float loss_acc = 0.f;
 
+    // item row / bias addresses: one table, or the owner shard's (possibly peer-mapped) memory
+    auto item_row = [&](int i, float *&row, float *&bias) {
+        if constexpr (PEER) {
+            int o, l;
+            shard_of(p, i, o, l);
+            row = p.Vp[o] + (int64_t)l * ld; bias = p.bp[o] + l;
+        } else {
+            row = p.V + (int64_t)i * ld; bias = p.b + i;
+        }
+    };
     auto load_rows = [&](Rows<VPL> &r, int u, int i, int j) {
         if (u >= 0) {
+            float *ri, *rj, *bi, *bj;
+            item_row(i, ri, bi); item_row(j, rj, bj);
             const float4 *pu = reinterpret_cast<const float4 *>(p.U + (int64_t)u * ld);
-            const float4 *pi = reinterpret_cast<const float4 *>(p.V + (int64_t)i * ld);
-            const float4 *pj = reinterpret_cast<const float4 *>(p.V + (int64_t)j * ld);
+            const float4 *pi = reinterpret_cast<const float4 *>(ri);
+            const float4 *pj = reinterpret_cast<const float4 *>(rj);
 #pragma unroll
             for (int v = 0; v < VPL; v++) {
                 r.u[v] = pu[v * G + gl];
-                r.vi[v] = pi[v * G + gl];
-                r.vj[v] = pj[v * G + gl];
+                r.vi[v] = PEER ? ld_sys_v4(pi + v * G + gl) : pi[v * G + gl];
+                r.vj[v] = PEER ? ld_sys_v4(pj + v * G + gl) : pj[v * G + gl];
             }
-            r.bi = p.b[i];
-            r.bj = p.b[j];
+            r.bi = *bi;
+            r.bj = *bj;
         }
     };
 
@@ -143,7 +168,8 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                     const float x = part + (cur.bi - cur.bj);
                     const float z = __fdividef(1.f, 1.f + __expf(x));  // BPRMF_model.py:98
                     if (gl == 0) loss_acc += fmaxf(-x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
-                    float *pu = p.U + (int64_t)cu * ld, *pi = p.V + (int64_t)ci * ld, *pj = p.V + (int64_t)cj * ld;
+                    float *pu = p.U + (int64_t)cu * ld, *pi, *pj, *pbi, *pbj;
+                    item_row(ci, pi, pbi); item_row(cj, pj, pbj);
 #pragma unroll
                     for (int v = 0; v < VPL; v++) {
                         const float4 a = cur.u[v], bi4 = cur.vi[v], bj4 = cur.vj[v];
@@ -163,7 +189,11 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                         dj.z = p.lr * (-un.z * z - p.reg_neg * bj4.z);
                         dj.w = p.lr * (-un.w * z - p.reg_neg * bj4.w);
                         const int e = (v * G + gl) * 4;
-                        if (ATOMIC) {
+                        if (PEER) {
+                            red_add_v4(pu + e, du);
+                            red_add_v4_sys(pi + e, di);
+                            red_add_v4_sys(pj + e, dj);
+                        } else if (ATOMIC) {
                             red_add_v4(pu + e, du);
                             red_add_v4(pi + e, di);
                             red_add_v4(pj + e, dj);
@@ -177,8 +207,9 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                     }
                     if (gl == 0) {
                         const float dbi = p.lr * (z - p.reg_b * cur.bi), dbj = p.lr * (-z - p.reg_b * cur.bj);
-                        if (ATOMIC) { red_add_f32(p.b + ci, dbi); red_add_f32(p.b + cj, dbj); }
-                        else { p.b[ci] = cur.bi + dbi; p.b[cj] = cur.bj + dbj; }
+                        if (PEER) { red_add_f32_sys(pbi, dbi); red_add_f32_sys(pbj, dbj); }
+                        else if (ATOMIC) { red_add_f32(pbi, dbi); red_add_f32(pbj, dbj); }
+                        else { *pbi = cur.bi + dbi; *pbj = cur.bj + dbj; }
                     }
                 }
             }
@@ -201,10 +232,10 @@ __global__ void __launch_bounds__(256) philox_sample_kernel(const HogwildParams 
     }
 }
 
-template <int DP, bool SAMPLE, bool ATOMIC>
+template <int DP, bool SAMPLE, bool ATOMIC, bool PEER = false>
 static int launch_hogwild_t(const HogwildParams &p, int reserve_sms, cudaStream_t st) {
     int per_sm = 0;
-    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bpr_hogwild_kernel<DP, SAMPLE, ATOMIC>, 256, 0));
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bpr_hogwild_kernel<DP, SAMPLE, ATOMIC, PEER>, 256, 0));
     if (per_sm < 1) per_sm = 1;
     int64_t tiles = (p.n + 31) / 32;
     int64_t want = (tiles + 7) / 8;
@@ -213,7 +244,7 @@ static int launch_hogwild_t(const HogwildParams &p, int reserve_sms, cudaStream_
     int64_t grid = (int64_t)sms * per_sm;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
-    bpr_hogwild_kernel<DP, SAMPLE, ATOMIC><<<(unsigned)grid, 256, 0, st>>>(p);
+    bpr_hogwild_kernel<DP, SAMPLE, ATOMIC, PEER><<<(unsigned)grid, 256, 0, st>>>(p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
@@ -231,6 +262,33 @@ static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_
         default: return set_err(EB_ERR_ARG, "row stride ld=%d must be one of 8,16,32,64,128,256 floats", dp);
     }
 #undef EB_CASE
+}
+
+// PEER mode: atomics only (other GPUs update the same rows), strides the sharded configurations use
+template <bool SAMPLE>
+static int launch_hogwild_peer(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
+    const int reserve = (flags >> 8) & 0xff;
+    switch (dp) {
+        case 32: return launch_hogwild_t<32, SAMPLE, true, true>(p, reserve, st);
+        case 64: return launch_hogwild_t<64, SAMPLE, true, true>(p, reserve, st);
+        case 128: return launch_hogwild_t<128, SAMPLE, true, true>(p, reserve, st);
+        default: return set_err(EB_ERR_ARG, "row stride ld=%d must be one of 32,64,128 floats for sharded item tables", dp);
+    }
+}
+
+static int fill_peer(HogwildParams &p, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
+                     int32_t n_items) {
+    EB_ARG(V_shards && b_shards && n_shards >= 1 && n_shards <= EB_MAX_PEERS, "1 <= n_shards <= %d", EB_MAX_PEERS);
+    EB_ARG(shard_rows >= 1 && (int64_t)shard_rows * n_shards >= n_items, "shards do not cover the item range");
+    for (int s = 0; s < n_shards; s++) {
+        EB_ARG(V_shards[s] && b_shards[s] && ((uintptr_t)V_shards[s] % 16) == 0, "null / misaligned shard pointer %d", s);
+        p.Vp[s] = V_shards[s]; p.bp[s] = b_shards[s];
+    }
+    for (int s = n_shards; s < EB_MAX_PEERS; s++) { p.Vp[s] = V_shards[0]; p.bp[s] = b_shards[0]; }
+    p.shard_rows = (uint32_t)shard_rows;
+    const uint64_t magic = (1ull << 32) / (uint64_t)shard_rows;       // shard_rows == 1 -> 2^32: clamp (the correction step covers it)
+    p.shard_magic = (uint32_t)(magic > 0xffffffffull ? 0xffffffffull : magic);
+    return EB_OK;
 }
 
 static int check_tables(const void *U, const void *V, const void *b, int d, int ld) {
@@ -425,6 +483,40 @@ extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
     return launch_hogwild<true>(p, ld, flags, (cudaStream_t)stream);
+}
+
+extern "C" int eb_bpr_step_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
+                                    int d, int ld, int32_t n_items, const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                                    float lr, float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int flags,
+                                    void *stream) {
+    EB_ARG(U && d >= 1 && ld >= d && ((uintptr_t)U % 16) == 0, "bad user table");
+    EB_ARG(n >= 0, "n < 0");
+    HogwildParams p{};
+    if (int rc = fill_peer(p, V_shards, b_shards, n_shards, shard_rows, n_items)) return rc;
+    if (n == 0) return EB_OK;
+    EB_ARG(tu && ti && tj, "null triple arrays");
+    p.U = U; p.ld = ld; p.tu = tu; p.ti = ti; p.tj = tj; p.n = n;
+    p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
+    return launch_hogwild_peer<false>(p, ld, flags, (cudaStream_t)stream);
+}
+
+extern "C" int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
+                                            int d, int ld, int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
+                                            const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple, float lr,
+                                            float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
+                                            int32_t *out_i, int32_t *out_j, int flags, void *stream) {
+    EB_ARG(U && d >= 1 && ld >= d && ((uintptr_t)U % 16) == 0, "bad user table");
+    EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
+    EB_ARG(csr_indptr && csr_indices, "null CSR");
+    EB_ARG((!out_u && !out_i && !out_j) || (out_u && out_i && out_j), "out_u/out_i/out_j: all or none");
+    HogwildParams p{};
+    if (int rc = fill_peer(p, V_shards, b_shards, n_shards, shard_rows, n_items)) return rc;
+    if (n == 0) return EB_OK;
+    p.U = U; p.ld = ld; p.n = n;
+    p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
+    p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
+    p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    return launch_hogwild_peer<true>(p, ld, flags, (cudaStream_t)stream);
 }
 
 extern "C" int eb_bpr_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,

@@ -80,4 +80,19 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 __device__ __forceinline__ void red_add_f32(float *p, float v) {
     asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// the same with system scope, for rows that may live in a PEER GPU's memory (NVLink atomics; REDG...STRONG.SYS)
+__device__ __forceinline__ void red_add_v4_sys(float *p, float4 v) {
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32_sys(float *p, float v) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// 128-bit load that must observe other GPUs' writes (no stale L1 line): LDG.E.128.STRONG.SYS
+__device__ __forceinline__ float4 ld_sys_v4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
 }  // namespace eb

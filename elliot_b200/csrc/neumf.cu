@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) neumf_gather_kernel(const float *Umf, con
 __global__ void __launch_bounds__(256) neumf_head_kernel(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f,
                                                          const float *wp, const float *bp, const float *label, int64_t n,
                                                          float *dpm, float *dh3, float *dwp, float *dbp, double *loss,
-                                                         float *prob_out) {
+                                                         float *prob_out, float invn) {
     const int lane = threadIdx.x & 31;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -55,7 +55,6 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *pm, int64_
 #pragma unroll
     for (int j = 0; j < 8; j++) acc_w[j] = 0.f;
     float acc_b = 0.f, acc_loss = 0.f;
-    const float invn = 1.f / (float)n;
     for (; w < n; w += nw) {
         float part = 0.f;
         for (int c = lane; c < 2 * f; c += 32) part += wp[c] * (c < f ? pm[w * ldp + c] : h3[w * ldh + c - f]);
@@ -198,16 +197,22 @@ extern "C" int eb_neumf_gather(const float *Umf, const float *Imf, const float *
     return EB_OK;
 }
 
-extern "C" int eb_neumf_head(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
-                             const float *label, int64_t n, float *dpm, float *dh3, float *dwp, float *dbp, double *loss,
-                             float *prob_out, void *stream) {
-    EB_ARG(pm && h3 && wp && bp && f >= 1 && f <= 128 && n >= 0, "bad argument");
+extern "C" int eb_neumf_head_norm(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
+                                  const float *label, int64_t n, int64_t mean_over, float *dpm, float *dh3, float *dwp, float *dbp,
+                                  double *loss, float *prob_out, void *stream) {
+    EB_ARG(pm && h3 && wp && bp && f >= 1 && f <= 128 && n >= 0 && mean_over >= 1, "bad argument");
     EB_ARG(!label || (dpm && dh3 && dwp && dbp), "training mode needs the gradient outputs");
     if (n == 0) return EB_OK;
     neumf_head_kernel<<<ngrid(n * 32), 256, 0, (cudaStream_t)stream>>>(pm, ldp, h3, ldh, f, wp, bp, label, n, dpm, dh3, dwp, dbp, loss,
-                                                                        prob_out);
+                                                                        prob_out, 1.f / (float)mean_over);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
+}
+
+extern "C" int eb_neumf_head(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
+                             const float *label, int64_t n, float *dpm, float *dh3, float *dwp, float *dbp, double *loss,
+                             float *prob_out, void *stream) {
+    return eb_neumf_head_norm(pm, ldp, h3, ldh, f, wp, bp, label, n, n > 0 ? n : 1, dpm, dh3, dwp, dbp, loss, prob_out, stream);
 }
 
 extern "C" int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream) {

@@ -74,36 +74,70 @@ class DataSet:
             self._mask = np.where(self.sp_i_train.toarray() == 0, True, False)
         return self._mask
 
-    # ---- kernel-side views -----------------------------------------------------------------
+    # ---- kernel-side views (thin wrappers; the models call the free functions below, which also work on the
+    # reference's own DataSet object when the plugin runs inside a real Elliot install) ----------------------
     def sampler_rows(self):
-        """The reference sampler's `_ui_dict` (custom_sampler.py:21): per user list(set(items))."""
-        return [list(set(self.i_train_dict[u])) for u in range(self.num_users)]
+        return sampler_rows_of(self)
 
     def train_csr(self, device):
-        """(indptr int64, set-order indices int32, sorted indices int32) on `device`."""
-        import torch
-        key = str(device)
-        if key not in self._dev:
-            rows = self.sampler_rows()
-            indptr = np.zeros(self.num_users + 1, np.int64)
-            indptr[1:] = np.cumsum([len(r) for r in rows])
-            flat = np.fromiter((x for r in rows for x in r), dtype=np.int32, count=int(indptr[-1]))
-            srt = np.fromiter((x for r in rows for x in sorted(r)), dtype=np.int32, count=int(indptr[-1]))
-            self._dev[key] = tuple(torch.from_numpy(a).to(device) for a in (indptr, flat, srt))
-        return self._dev[key]
+        return train_csr_of(self, device)
 
     def eval_csr(self, which="test"):
-        """Host CSR (indptr, private item ids, gains) of the relevant items per private user."""
-        d = self.test_dict if which == "test" else getattr(self, "val_dict", None)
-        if d is None:
-            return None
-        thr = self.config.evaluation.relevance_threshold
-        indptr = np.zeros(self.num_users + 1, np.int64)
-        idx, gain = [], []
-        for pu, u in enumerate(self.users):
-            for it, score in d.get(u, {}).items():
-                if score >= thr:
-                    idx.append(self.public_items.get(it, -1))       # test-only items can never be recommended
-                    gain.append(2 ** (score - thr + 1) - 1)          # relevance.py:80-82
-            indptr[pu + 1] = len(idx)
-        return indptr, np.array(idx, np.int64), np.array(gain, np.float64)
+        return eval_csr_of(self, which)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Kernel-side views of ANY object with the reference DataSet's fields (dataset.py:199-245): `i_train_dict`,
+# `sp_i_train`, `users`, `public_items`, `test_dict` / `val_dict`, `config`.  They are free functions on purpose:
+# inside a real Elliot install `self._data` is elliot.dataset.dataset.DataSet, which has none of the mirror's
+# helper methods (the drop-in path must not depend on them).
+# ---------------------------------------------------------------------------------------------------
+def sampler_rows_of(data):
+    """The reference sampler's `_ui_dict` (custom_sampler.py:21): per private user list(set(items)) — CPython set
+    order, needed only where the reference's MT19937 stream is replayed (exact mode)."""
+    return [list(set(data.i_train_dict[u])) for u in range(len(data.users))]
+
+
+def train_csr_of(data, device, set_order=True):
+    """(indptr int64, set-order indices int32 or None, sorted indices int32) on `device`, cached on the data object.
+    The sorted CSR comes straight from `sp_i_train` (scipy, C speed — no per-row Python); the set-order copy is built
+    row by row in Python because it IS CPython's set iteration order (exact mode only; set_order=False skips it)."""
+    import torch
+    cache = data.__dict__.setdefault("_eb200_dev", {})
+    key = (str(device), bool(set_order))
+    if key not in cache:
+        other = cache.get((str(device), True))
+        if other is not None:                                        # the full triple covers the partial request
+            cache[key] = other
+            return other
+        m = data.sp_i_train.tocsr()
+        if not m.has_sorted_indices:
+            m = m.sorted_indices()
+        indptr = m.indptr.astype(np.int64)
+        srt = m.indices.astype(np.int32)
+        flat = None
+        if set_order:
+            rows = sampler_rows_of(data)
+            flat = np.fromiter((x for r in rows for x in r), dtype=np.int32, count=int(indptr[-1]))
+            assert all(len(r) == indptr[u + 1] - indptr[u] for u, r in enumerate(rows)), "sp_i_train and i_train_dict disagree"
+        cache[key] = tuple(None if a is None else torch.from_numpy(a).to(device) for a in (indptr, flat, srt))
+    return cache[key]
+
+
+def eval_csr_of(data, which="test"):
+    """Host CSR (indptr, private item ids, gains) of the relevant items per private user (evaluator.py:117-147,
+    relevance.py:80-82); None when the split does not exist."""
+    d = data.test_dict if which == "test" else getattr(data, "val_dict", None)
+    if d is None:
+        return None
+    thr = data.config.evaluation.relevance_threshold
+    n_users = len(data.users)
+    indptr = np.zeros(n_users + 1, np.int64)
+    idx, gain = [], []
+    for pu, u in enumerate(data.users):
+        for it, score in d.get(u, {}).items():
+            if score >= thr:
+                idx.append(data.public_items.get(it, -1))            # test-only items can never be recommended
+                gain.append(2 ** (score - thr + 1) - 1)              # relevance.py:80-82
+        indptr[pu + 1] = len(idx)
+    return indptr, np.array(idx, np.int64), np.array(gain, np.float64)

@@ -13,6 +13,8 @@ import math
 
 import numpy as np
 
+from .dataset import eval_csr_of
+
 SUPPORTED = {"ndcg": "nDCG", "hr": "HR", "precision": "Precision", "recall": "Recall"}
 
 
@@ -30,7 +32,7 @@ class Evaluator:
                 raise Exception(f"metric {m} is not available in elliot_b200's evaluator "
                                 f"(use the reference Evaluator through ProxyRecommender for the other 40)")
             self._metrics.append(SUPPORTED[m.lower()])
-        self._sets = {"test": data.eval_csr("test"), "val": data.eval_csr("val")}
+        self._sets = {"test": eval_csr_of(data, "test"), "val": eval_csr_of(data, "val")}
 
     def get_needed_recommendations(self):
         return self._data.config.top_k

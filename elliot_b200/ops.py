@@ -395,10 +395,11 @@ def neumf_gather(Umf, Imf, Umlp, Imlp, f, u, it, x0, pm):
           _ptr(x0), x0.stride(0), _ptr(pm), pm.stride(0))
 
 
-def neumf_head(pm, h3, f, wp, bp, label=None, dpm=None, dh3=None, dwp=None, dbp=None, loss=None, prob=None):
+def neumf_head(pm, h3, f, wp, bp, label=None, dpm=None, dh3=None, dwp=None, dbp=None, loss=None, prob=None, mean_over=None):
+    """mean_over: number of samples the BinaryCrossentropy mean runs over (default: this call's batch)."""
     _need_cuda(pm, h3, wp, bp, label, dpm, dh3, dwp, dbp, loss, prob)
-    _call("eb_neumf_head", pm, _ptr(pm), pm.stride(0), _ptr(h3), h3.stride(0), f, _ptr(wp), _ptr(bp), _ptr(label), pm.shape[0],
-          _ptr(dpm), _ptr(dh3), _ptr(dwp), _ptr(dbp), _ptr(loss), _ptr(prob))
+    _call("eb_neumf_head_norm", pm, _ptr(pm), pm.stride(0), _ptr(h3), h3.stride(0), f, _ptr(wp), _ptr(bp), _ptr(label), pm.shape[0],
+          int(mean_over) if mean_over else max(int(pm.shape[0]), 1), _ptr(dpm), _ptr(dh3), _ptr(dwp), _ptr(dbp), _ptr(loss), _ptr(prob))
 
 
 def relu_bwd(dout, out):
@@ -547,3 +548,72 @@ def bpr_step_rows_f32(U, tu, Ri, Rj, bias_col, lr, reg_u, reg_b, reg_pos, reg_ne
     _call("eb_bpr_step_rows_f32", U, _ptr(U), U.stride(0), _ptr(tu), _ptr(Ri), _ptr(Rj), Ri.stride(0), tu.numel(), bias_col,
           lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(dRi), _ptr(dRj), _ptr(loss))
     return dRi, dRj
+
+
+# ---------------------------------------------------------------- peer-addressed tables (csrc/peer.cu, bpr_train.cu PEER mode)
+def _ptr_array(ptrs):
+    """HOST array of device addresses (the `*_shards` arguments of the C ABI): ints, tensors, or a ready ctypes array."""
+    if isinstance(ptrs, ctypes.Array):
+        return ptrs, len(ptrs)
+    vals = [p.data_ptr() if torch.is_tensor(p) else int(p) for p in ptrs]
+    return (ctypes.c_void_p * len(vals))(*vals), len(vals)
+
+
+def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None):
+    """BPR step on materialised triples, item table + biases row-sharded (shard s = rows [s*shard_rows, (s+1)*shard_rows))."""
+    _need_cuda(U, tu, ti, tj, loss); _chk_idx(tu, ti, tj)
+    va, n = _ptr_array(V_shards); ba, nb = _ptr_array(b_shards)
+    assert n == nb and U.dtype == torch.float32 and U.stride(1) == 1
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_peer_f32(_ptr(U), va, ba, n, shard_rows, d, U.stride(0), n_items, _ptr(tu), _ptr(ti), _ptr(tj),
+                                         tu.numel(), lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), 0, _stream(U)))
+
+
+def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u,
+                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0):
+    """Fused sample+update step with the item table row-sharded over the GPUs of the box (loads / atomics over NVLink)."""
+    _need_cuda(U, indptr, indices, loss)
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and U.dtype == torch.float32 and U.stride(1) == 1
+    va, ns = _ptr_array(V_shards); ba, nb = _ptr_array(b_shards)
+    assert ns == nb
+    ou = oi = oj = None
+    if out is not None:
+        ou, oi, oj = out
+        _need_cuda(ou, oi, oj); _chk_idx(ou, oi, oj)
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_sampled_peer_f32(_ptr(U), va, ba, ns, shard_rows, d, U.stride(0), n_users, n_items, _ptr(indptr),
+                                                 _ptr(indices), n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss),
+                                                 _ptr(ou), _ptr(oi), _ptr(oj), (int(reserve_sms) & 0xff) << 8, _stream(U)))
+
+
+def table_reconcile_peer_f32(slice_ptrs, prev_slice, scale, max_ctas=0):
+    """One-kernel reconciliation of a replicated table's slice (see eb_table_reconcile_peer_f32)."""
+    _need_cuda(prev_slice)
+    pa, n = _ptr_array(slice_ptrs)
+    with torch.cuda.device(prev_slice.device):
+        check(lib().eb_table_reconcile_peer_f32(pa, n, _ptr(prev_slice), prev_slice.numel(), float(scale), int(max_ctas),
+                                                _stream(prev_slice)))
+
+
+def neumf_gather_peer(Umf, Umlp, I_shards, shard_rows, ldi, f, u, it, x0, pm):
+    _need_cuda(Umf, Umlp, u, it, x0, pm)
+    ia, n = _ptr_array(I_shards)
+    _call("eb_neumf_gather_peer", Umf, _ptr(Umf), _ptr(Umlp), Umf.stride(0), ia, n, shard_rows, ldi, f, _ptr(u), _ptr(it), u.numel(),
+          _ptr(x0), x0.stride(0), _ptr(pm), pm.stride(0))
+
+
+def neumf_scatter_peer(Umf, I_shards, GI_shards, shard_rows, ldi, f, u, it, dpm, dx0, dUmf, dUmlp):
+    _need_cuda(Umf, u, it, dpm, dx0, dUmf, dUmlp)
+    ia, n = _ptr_array(I_shards); ga, ng = _ptr_array(GI_shards)
+    assert n == ng
+    _call("eb_neumf_scatter_peer", Umf, _ptr(Umf), Umf.stride(0), ia, ga, n, shard_rows, ldi, f, _ptr(u), _ptr(it), u.numel(),
+          _ptr(dpm), dpm.stride(0), _ptr(dx0), dx0.stride(0), _ptr(dUmf), _ptr(dUmlp))
+
+
+def gather_rows_peer_f32(shards, shard_rows, ld, ids, width, out=None):
+    _need_cuda(ids, out); _chk_idx(ids)
+    sa, n = _ptr_array(shards)
+    if out is None:
+        out = torch.empty((ids.numel(), width), dtype=torch.float32, device=ids.device)
+    _call("eb_gather_rows_peer_f32", ids, sa, n, shard_rows, ld, _ptr(ids), ids.numel(), width, _ptr(out), out.stride(0))
+    return out

@@ -254,3 +254,85 @@ def gather_topk(idx_local, val_local, n_users, group=None):
     dist.all_gather(out_i, padded(idx_local, -1), group=group)
     dist.all_gather(out_v, padded(val_local, float("-inf")), group=group)
     return (torch.cat([t[:n] for t, n in zip(out_i, sizes)]), torch.cat([t[:n] for t, n in zip(out_v, sizes)]))
+
+
+# ---------------------------------------------------------------- peer-addressed tables (one NVSwitch box)
+def ceil_shard(n_rows, world):
+    """Equal shards of ceil(n_rows / world) rows (the last may be short): owner = row // shard_rows — what the
+    kernels of csrc/peer.cu compute with one multiply-high."""
+    return -(-int(n_rows) // int(world))
+
+
+class PeerShardedTable:
+    """A [n_rows, ld] fp32 table row-sharded over the ranks in memory every rank can address (peer.PeerBuffer).
+    `local` = this rank's shard (rows [lo, hi) in its first hi-lo rows), `ptrs` = every shard's device address as
+    seen from this process — the `*_shards` argument of the PEER kernels (ops.bpr_step_sampled_peer_f32,
+    ops.neumf_gather_peer, ...), which read and atomically update rows in their owner's memory over NVLink: there is
+    no fetch/push step and no all-to-all."""
+
+    def __init__(self, n_rows, ld, group=None, device=None, buffer_cls=None):
+        from .peer import PeerBuffer
+        self.n_rows, self.ld, self.group = int(n_rows), int(ld), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.shard_rows = ceil_shard(n_rows, self.world)
+        self.lo = min(self.rank * self.shard_rows, self.n_rows)
+        self.hi = min(self.lo + self.shard_rows, self.n_rows)
+        self.buf = (buffer_cls or PeerBuffer)(self.shard_rows * self.ld, group=group, device=device)
+        self.local = self.buf.local.view(self.shard_rows, self.ld)
+        self.ptrs = self.buf.ptr_array()
+
+    def load_from_full(self, full):
+        """Copy this rank's rows out of a full [n_rows, ld] table (init / tests)."""
+        self.local[:self.hi - self.lo].copy_(full[self.lo:self.hi])
+
+    def all_rows(self):
+        """The whole table gathered on this rank (scoring over sharded item tables): one kernel reading every shard."""
+        from . import ops
+        ids = torch.arange(self.n_rows, dtype=torch.int32, device=self.local.device)
+        return ops.gather_rows_peer_f32(self.ptrs, self.shard_rows, self.ld, ids, self.ld)
+
+    def barrier(self):
+        self.buf.barrier()
+
+    def close(self):
+        self.local = None
+        self.buf.close()
+
+
+class PeerTableSync:
+    """Replicated table (every rank trains on its own copy, which lives in a peer.PeerBuffer) kept consistent by ONE
+    kernel per rank and step instead of delta-kernel -> NCCL all-reduce -> apply-kernel: rank r owns the r-th slice,
+    reads that slice of every copy over NVLink, agrees on the mean (or sum) of the copies' steps since the slice's
+    last agreed value and pushes each copy's correction back with vector atomics (ops.table_reconcile_peer_f32).
+    The correction is atomic and per element, so training kernels may run on any copy meanwhile: nothing is lost,
+    nothing is counted twice, no rank ever waits for another (ReplicatedTableSync semantics, asynchronously)."""
+
+    def __init__(self, buf, numel=None, reduce="mean", max_ctas=0):
+        from . import ops
+        assert reduce in ("mean", "sum")
+        self.buf, self.ops = buf, ops
+        self.numel = int(numel if numel is not None else buf.numel)
+        assert self.numel % 4 == 0 and self.numel <= buf.numel
+        lo4, hi4 = shard_range(self.numel // 4, buf.rank, buf.world)
+        self.lo, self.hi = 4 * lo4, 4 * hi4
+        self.scale = 1.0 / buf.world if reduce == "mean" else 1.0
+        self.max_ctas = max_ctas
+        self.slice_ptrs = buf.ptr_array(self.lo)
+        self.prev = buf.local[self.lo:self.hi].clone()
+
+    def reset(self):
+        """Collective: re-baseline on the copies' current contents (they must already agree)."""
+        self.buf.barrier()
+        self.prev.copy_(self.buf.local[self.lo:self.hi])
+        self.buf.barrier()
+
+    def sync(self):
+        if self.hi > self.lo:
+            self.ops.table_reconcile_peer_f32(self.slice_ptrs, self.prev, self.scale, self.max_ctas)
+
+    def flush(self):
+        """Collective: after every rank stopped training, one more round makes all copies equal."""
+        self.buf.barrier()
+        self.sync()
+        self.buf.barrier()

@@ -1,7 +1,6 @@
-"""Plugin entry module for the reference's `external_models_path` mechanism
-(elliot/run.py:67-73, docs/source/guide/new_alg.rst): point the YAML at this file and name the
-models `external.BPRMF`, ...  In a real Elliot install the classes derive from Elliot's own
-BaseRecommenderModel (see recommender/_bases.py)."""
+"""Older name of the plugin entry module; the reference-facing entry point is elliot_b200/external/__init__.py (it must
+be a package `__init__.py` for the reference's logger lookup to work, see there).  Kept so that stand-alone configs
+that point `external_models_path` at this file keep working with elliot_b200.run."""
 import os
 import sys
 

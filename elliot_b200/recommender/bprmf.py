@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..dataset import train_csr_of
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
 
 
@@ -144,7 +145,7 @@ class BPRMF(RecMixin, BaseRecommenderModel):
         self._model = MFModel(self._factors, self._data, self._learning_rate, self._user_regularization,
                               self._bias_regularization, self._positive_item_regularization,
                               self._negative_item_regularization, self._seed, mode=self._mode, device=self._device)
-        self._indptr, self._set_idx, self._sorted_idx = self._data.train_csr(self._device)
+        self._indptr, self._set_idx, self._sorted_idx = train_csr_of(self._data, self._device)
         self._sampler = ops.MtSampler(self._num_users, self._num_items, self._indptr, self._set_idx,
                                       self._sorted_idx, seed=42)     # custom_sampler.py:15
         np.random.seed(42)                                      # keep the host's global stream where the reference leaves it

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..dataset import train_csr_of
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
 
 
@@ -103,7 +104,7 @@ class BPRMF_batch(RecMixin, BaseRecommenderModel):
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.BPRMF_batch needs a CUDA device (there is no CPU fallback)")
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
-        self._indptr, self._set_idx, self._sorted_idx = self._data.train_csr(self._device)
+        self._indptr, self._set_idx, self._sorted_idx = train_csr_of(self._data, self._device)
         self._sampler = ops.MtSampler(self._num_users, self._num_items, self._indptr, self._set_idx, self._sorted_idx, seed=42)
         self._model = BPRMFBatchModel(self._factors, self._learning_rate, self._l_w, self._l_b, self._num_users,
                                       self._num_items, self._seed, self._device)

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..dataset import train_csr_of
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
 
 
@@ -136,7 +137,7 @@ class MF2020(RecMixin, BaseRecommenderModel):
         self._model = MF2020Model(self._factors, self._data, self._learning_rate, self._regularization, self._seed,
                                   mode=self._mode, device=self._device)
         self._sampler = RendleSampler(self._data.sp_i_train, self._m, self._seed, self._model.np_stream)
-        self._indptr, _, self._sorted_idx = self._data.train_csr(self._device)
+        self._indptr, _, self._sorted_idx = train_csr_of(self._data, self._device, set_order=False)
         self._pos_u = torch.from_numpy(self._sampler.pos_u).to(self._device)
         self._pos_i = torch.from_numpy(self._sampler.pos_i).to(self._device)
         self._loss_dev = torch.zeros(1, dtype=torch.float64, device=self._device)

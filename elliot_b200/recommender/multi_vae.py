@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..dataset import train_csr_of
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
 
 
@@ -215,7 +216,7 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
         self._dp = bool(getattr(self._params, "b200_dp", False))
         default_dev = f"cuda:{os.environ.get('LOCAL_RANK', '0')}" if self._dp else "cuda:0"
         self._device = torch.device(getattr(self._params, "b200_device", default_dev))
-        self._indptr, _, self._sorted_idx = self._data.train_csr(self._device)
+        self._indptr, _, self._sorted_idx = train_csr_of(self._data, self._device, set_order=False)
         self._model = VariationalAutoEncoder(self._num_items, self._intermediate_dim, self._latent_dim, self._learning_rate,
                                              self._dropout_rate, self._lambda, self._seed, self._indptr, self._sorted_idx,
                                              self._device)

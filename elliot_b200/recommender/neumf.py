@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..dataset import train_csr_of
 from ._bases import BaseRecommenderModel, RecMixin, init_charger
 
 
@@ -177,7 +178,7 @@ class NeuMF(RecMixin, BaseRecommenderModel):
             raise RuntimeError("elliot_b200.NeuMF needs a CUDA device (there is no CPU fallback)")
         self._ratings = self._data.train_dict
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
-        self._indptr, _, self._sorted_idx = self._data.train_csr(self._device)
+        self._indptr, _, self._sorted_idx = train_csr_of(self._data, self._device, set_order=False)
         self._model = NeuralMatrixFactorizationModel(self._num_users, self._num_items, self._mf_factors, self._learning_rate,
                                                      self._seed, self._device)
         self._gen = torch.Generator(device=self._device); self._gen.manual_seed(42)

@@ -213,6 +213,11 @@ int eb_neumf_gather(const float *Umf, const float *Imf, const float *Umlp, const
 int eb_neumf_head(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
                   const float *label, int64_t n, float *dpm, float *dh3, float *dwp, float *dbp, double *loss,
                   float *prob_out, void *stream);
+/* the same with the BinaryCrossentropy mean taken over `mean_over` samples instead of the n passed in (a rank's slice of
+ * a global batch: the loss and every gradient root are scaled by 1/mean_over) */
+int eb_neumf_head_norm(const float *pm, int64_t ldp, const float *h3, int64_t ldh, int f, const float *wp, const float *bp,
+                       const float *label, int64_t n, int64_t mean_over, float *dpm, float *dh3, float *dwp, float *dbp,
+                       double *loss, float *prob_out, void *stream);
 int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
 int eb_neumf_scatter(const float *Umf, const float *Imf, int f, int64_t ldt, const int32_t *u, const int32_t *it, int64_t n,
                      const float *dpm, int64_t ldp, const float *dx0, int64_t ldx, float *dUmf, float *dImf, float *dUmlp,
@@ -313,6 +318,62 @@ int eb_scatter_add_rows_f32(float *table, int64_t ld, const int32_t *ids, int64_
 int eb_bpr_step_rows_f32(float *U, int64_t ldu, const int32_t *tu, const float *Ri, const float *Rj, int64_t ldr, int64_t n,
                          int bias_col, float lr, float reg_u, float reg_b, float reg_pos, float reg_neg, float *dRi,
                          float *dRj, double *loss, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Tables spread over the GPUs of one NVSwitch box, addressed DIRECTLY by the kernels (SURVEY.md §8e;
+ * no reference counterpart: the reference is single-device).  One process per GPU: a rank allocates its
+ * part with eb_peer_alloc (the one place this library allocates: the memory must be a plain cudaMalloc
+ * block to be exportable; zero-filled), publishes its 64-byte CUDA IPC handle (eb_peer_export; the host
+ * exchanges the handles, e.g. with torch.distributed.all_gather_object) and maps the other ranks' parts
+ * (eb_peer_open, peer access enabled lazily).  `*_shards` / `slice_ptrs` arguments below are HOST arrays of
+ * n device pointers, entry r = rank r's part as seen from the calling process (its own allocation for
+ * r = own rank).  Row i of a sharded table lives in shard i / shard_rows at local row i % shard_rows.
+ * ------------------------------------------------------------------------ */
+#define EB_MAX_PEERS 8
+int eb_peer_alloc(size_t bytes, void **dev_ptr);
+int eb_peer_free(void *dev_ptr);
+int eb_peer_export(const void *dev_ptr, void *handle64_host);
+int eb_peer_open(const void *handle64_host, void **dev_ptr);
+int eb_peer_close(void *dev_ptr);
+
+/* BPR step (BPRMF_model.py:91-117 arithmetic, as eb_bpr_step_f32 / eb_bpr_step_sampled_f32) with the ITEM table and
+ * item biases row-sharded over n_shards GPUs: user rows are local (a rank samples only for the users it owns,
+ * custom_sampler.py:31-42 distribution over ITS users), item rows are loaded from and updated in their owner's
+ * memory over NVLink (128-bit loads, system-scope red.add.v4.f32) inside the one training kernel — the
+ * three all-to-alls of an NCCL formulation never happen.  ld in {32, 64, 128}. */
+int eb_bpr_step_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
+                         int d, int ld, int32_t n_items, const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n,
+                         float lr, float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int flags,
+                         void *stream);
+int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
+                                 int d, int ld, int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
+                                 const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple, float lr,
+                                 float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
+                                 int32_t *out_i, int32_t *out_j, int flags, void *stream);
+
+/* REPLICATED table kept consistent without a collective: the caller owns one slice of the table; slice_ptrs[p] is
+ * the address of that slice inside rank p's copy (n floats, n % 4 == 0), prev_slice the slice's last agreed value
+ * (local, n floats).  One kernel: agreed = scale * sum_p (copy_p - prev); every copy += agreed - (copy_p - prev)
+ * (vector atomics, so training kernels running on any copy at the same time lose nothing); prev += agreed.
+ * scale = 1/n_peers averages the ranks' steps (local-SGD style), scale = 1 sums them.  max_ctas > 0 caps the grid
+ * (to run beside a training kernel). */
+int eb_table_reconcile_peer_f32(float *const *slice_ptrs, int n_peers, float *prev_slice, int64_t n, float scale,
+                                int max_ctas, void *stream);
+
+/* NeuMF (neural_matrix_factorization_model.py:74-106) with the two ITEM tables side by side in one row-sharded
+ * [items, ldi >= 2f] table (row = [I_mf | I_mlp]) and user tables local: eb_neumf_gather / eb_neumf_scatter with the
+ * item rows read from, and the item-row gradients added into, the owner's memory (GI_shards: the owners' dense
+ * gradient shards, same layout). */
+int eb_neumf_gather_peer(const float *Umf, const float *Umlp, int64_t ldu, float *const *I_shards, int n_shards,
+                         int32_t shard_rows, int64_t ldi, int f, const int32_t *u, const int32_t *it, int64_t n, float *x0,
+                         int64_t ldx, float *pm, int64_t ldp, void *stream);
+int eb_neumf_scatter_peer(const float *Umf, int64_t ldu, float *const *I_shards, float *const *GI_shards, int n_shards,
+                          int32_t shard_rows, int64_t ldi, int f, const int32_t *u, const int32_t *it, int64_t n,
+                          const float *dpm, int64_t ldp, const float *dx0, int64_t ldx, float *dUmf, float *dUmlp,
+                          void *stream);
+/* out[t][0..width) = row ids[t] of a sharded table (scoring over sharded item tables, tests) */
+int eb_gather_rows_peer_f32(float *const *shards, int n_shards, int32_t shard_rows, int64_t ld, const int32_t *ids, int64_t n,
+                            int width, float *out, int64_t ldo, void *stream);
 
 /* Tensor-core path (tcgen05 + TMEM + TMA, bf16 mainloop, exact fp32 re-rank).  Same contract and
  * same RESULT as eb_score_topk_f32 (identical index lists and scores): the kernel keeps the 32
