@@ -22,6 +22,7 @@ struct ScoreParams {
     const int32_t *mask_indices;
     const int32_t *users;
     const int32_t *positions;  // optional: row q works on user_begin+positions[q] and writes output row positions[q]
+    const int32_t *n_rows_dev; // optional: number of rows actually present (device side), <= n_sel
     int32_t user_begin;
     int64_t n_sel;
     int k;
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(const ScoreParams
     __shared__ int win_i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *s = p.scratch + (int64_t)blockIdx.x * p.n_items;
-    for (int64_t q = blockIdx.x; q < p.n_sel; q += gridDim.x) {
+    const int64_t n_rows = p.n_rows_dev ? min((int64_t)*p.n_rows_dev, p.n_sel) : p.n_sel;
+    for (int64_t q = blockIdx.x; q < n_rows; q += gridDim.x) {
         const int64_t qo = p.positions ? (int64_t)p.positions[q] : q;
         const int u = p.users ? p.users[q] : p.user_begin + (int)qo;
         __syncthreads();
@@ -124,7 +126,8 @@ template <typename T>
 static int score_topk_exact(const T *U, const T *V, const T *bias, int32_t n_items, int d, int ld,
                             const int64_t *mask_indptr, const int32_t *mask_indices, const int32_t *users,
                             int32_t user_begin, int64_t n_sel, int k, int32_t *out_idx, T *out_val, void *workspace,
-                            size_t workspace_bytes, void *stream, const int32_t *positions = nullptr) {
+                            size_t workspace_bytes, void *stream, const int32_t *positions = nullptr,
+                            const int32_t *n_rows_dev = nullptr) {
     EB_ARG(U && V && out_idx && out_val, "null pointer");
     EB_ARG(d >= 1 && ld >= d && n_items >= 1 && k >= 1, "bad shape d=%d ld=%d n_items=%d k=%d", d, ld, n_items, k);
     EB_ARG((mask_indptr == nullptr) == (mask_indices == nullptr), "mask CSR: both or neither");
@@ -134,8 +137,8 @@ static int score_topk_exact(const T *U, const T *V, const T *bias, int32_t n_ite
     if (workspace_bytes < row || !workspace)
         return set_err(EB_ERR_WORKSPACE, "workspace %zu < one score row %zu", workspace_bytes, row);
     if ((size_t)ctas * row > workspace_bytes) ctas = (int64_t)(workspace_bytes / row);
-    ScoreParams<T> p{U, V, bias, n_items, d, ld, mask_indptr, mask_indices, users, positions, user_begin, n_sel, k, out_idx, out_val,
-                     (T *)workspace};
+    ScoreParams<T> p{U, V, bias, n_items, d, ld, mask_indptr, mask_indices, users, positions, n_rows_dev, user_begin, n_sel, k, out_idx,
+                     out_val, (T *)workspace};
     score_topk_exact_kernel<T><<<(unsigned)ctas, 256, sizeof(T) * (size_t)d, (cudaStream_t)stream>>>(p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
@@ -171,4 +174,14 @@ extern "C" int eb_score_topk_f32_mapped(const float *U, const float *V, const fl
                                         void *stream) {
     return eb::score_topk_exact<float>(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, nullptr, user_begin,
                                        n_sel, k, out_idx, out_val, workspace, workspace_bytes, stream, positions);
+}
+
+extern "C" int eb_score_topk_f32_mapped_dev(const float *U, const float *V, const float *item_bias, int32_t n_items, int d,
+                                            int ld, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                            const int32_t *positions, const int32_t *n_rows_dev, int32_t user_begin,
+                                            int64_t n_sel_max, int k, int32_t *out_idx, float *out_val, void *workspace,
+                                            size_t workspace_bytes, void *stream) {
+    EB_ARG(positions && n_rows_dev, "null pointer");
+    return eb::score_topk_exact<float>(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, nullptr, user_begin,
+                                       n_sel_max, k, out_idx, out_val, workspace, workspace_bytes, stream, positions, n_rows_dev);
 }

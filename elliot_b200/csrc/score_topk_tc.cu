@@ -124,6 +124,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// K tail (KP % 64 = 16 or 32 columns): the same K-major tile with a 32-byte (layout 6) or 64-byte (layout 4) swizzle,
+// as TMA SWIZZLE_32B / SWIZZLE_64B writes a {16 | 32 bf16, rows} box: rows 32 / 64 B apart, 8-row groups 256 / 512 B apart.
+template <int KT>
+__device__ __forceinline__ uint64_t umma_desc_tail(uint32_t smem_addr) {
+    constexpr uint64_t sbo = KT == 16 ? 16 : 32, layout = KT == 16 ? 6 : 4;
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
@@ -160,20 +167,28 @@ struct TcParams {
 constexpr int TC_BUF = 64;        // append buffer per user row (top-KC kept + up to BUF-KC pending)
 constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 columns if fewer than 8 slots are free
 
+// KP = padded K (multiple of 16): KB full 64-wide blocks (one 128-byte swizzle atom each) + a tail of KT = 0, 16 or 32
+// columns in its own narrower-swizzle block.  (A 48-column tail is rounded up to a full block by the host.)  Padding K
+// to a multiple of 64 instead — as round 1 did — costs 2.0x the MMA work at d = 64 + 2 bias columns (128 vs 80) and
+// 1.33x at d = 128 + 2 (192 vs 144).
 template <int KP> struct TcCfg {
-    static constexpr int KB = KP / 64;                       // 64-wide K blocks (one swizzle atom each)
+    static constexpr int KB = KP / 64;                       // full 64-wide K blocks
+    static constexpr int KT = KP % 64;                       // tail columns
+    static_assert(KT == 0 || KT == 16 || KT == 32, "K tail must be 0, 16 or 32 columns");
     // Epilogue warpgroups.  NG = 2 (tile-parity split, two candidate lists per row merged per user block) is
     // implemented and exact, but measured no faster than NG = 1 on B200: each half-stream has a lower threshold
     // (1.85x more inserts) and the smaller B tiles it forces cost more than the extra warps gain.
     static constexpr int NG = 1;
-    static constexpr int BN = NG == 2 ? (KP == 64 ? 256 : (KP == 128 ? 128 : 64))
-                                      : (KP <= 128 ? 256 : (KP == 192 ? 128 : 64));   // items per tile (UMMA N)
-    static constexpr int STAGES = (NG == 1 && KP == 64) ? 3 : 2;
+    static constexpr int BN = KP <= 128 ? 256 : (KP <= 208 ? 128 : 64);                   // items per tile (UMMA N)
     static constexpr int THREADS = 64 + 128 * NG;            // TMA warp + MMA warp + NG x 4 epilogue warps
     static constexpr int A_BYTES = TC_BM * KP * 2;
     static constexpr int B_BYTES = BN * KP * 2;
     static constexpr int CAND_BYTES = NG * TC_BM * TC_BUF * 8;
-    static constexpr int SMEM = A_BYTES + STAGES * B_BYTES + CAND_BYTES + 1024 /*merged cnt/thresh*/ + 256;
+    static constexpr int FIXED = A_BYTES + CAND_BYTES + 1024 /*merged cnt/thresh*/ + 256;
+    static constexpr int ROOM = (232448 - FIXED) / B_BYTES;  // 227 KB of dynamic shared memory per CTA
+    static constexpr int STAGES = ROOM >= 4 ? 4 : ROOM;
+    static_assert(STAGES >= 2, "B ring needs two stages");
+    static constexpr int SMEM = FIXED + STAGES * B_BYTES;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -259,11 +274,13 @@ __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint
     return make_uint2((uint32_t)cnt, __float_as_uint(thresh));
 }
 
-template <int KP, bool DUMP, bool HAS_BIAS>
+template <int KP, bool HAS_BIAS>
 __global__ void __launch_bounds__(TcCfg<KP>::THREADS, 1)
-score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmBt, const TcParams p) {
     using C = TcCfg<KP>;
-    constexpr int KB = C::KB, BN = C::BN, S = C::STAGES, NG = C::NG;
+    constexpr int KB = C::KB, KT = C::KT, BN = C::BN, S = C::STAGES, NG = C::NG;
+    const bool DUMP = p.dump != nullptr;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
     uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
@@ -289,6 +306,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        if (KT) { tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmBt); }
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
     tc_fence_before();
@@ -305,11 +323,13 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_expect_tx(A_FULL, C::A_BYTES);
                 for (int kb = 0; kb < KB; kb++)
                     tma_load_2d(smem_u32(sA + kb * (TC_BM * 128)), &tmA, A_FULL, kb * 64, mb * TC_BM);
+                if (KT) tma_load_2d(smem_u32(sA + KB * (TC_BM * 128)), &tmAt, A_FULL, KB * 64, mb * TC_BM);
                 for (int t = 0; t < n_tiles; t++) {
                     mbar_wait(B_EMPTY(s), ph ^ 1);
                     mbar_expect_tx(B_FULL(s), C::B_BYTES);
                     for (int kb = 0; kb < KB; kb++)
                         tma_load_2d(smem_u32(sB + s * C::B_BYTES + kb * (BN * 128)), &tmB, B_FULL(s), kb * 64, t * BN);
+                    if (KT) tma_load_2d(smem_u32(sB + s * C::B_BYTES + KB * (BN * 128)), &tmBt, B_FULL(s), KB * 64, t * BN);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
@@ -335,6 +355,14 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int k = 0; k < 4; k++)   // UMMA_K = 16 bf16 = 32 B inside the 128-B swizzle atom
                             umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                                       (kb | k) != 0);
+                    }
+                    if (KT) {                         // K tail: one (16 columns) or two (32) more K = 16 steps
+                        const uint32_t a_addr = smem_u32(sA + KB * (TC_BM * 128));
+                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + KB * (BN * 128));
+#pragma unroll
+                        for (int k = 0; k < KT / 16; k++)
+                            umma_bf16(d_tmem, umma_desc_tail<KT ? KT : 16>(a_addr + k * 32), umma_desc_tail<KT ? KT : 16>(b_addr + k * 32),
+                                      idesc, (KB | k) != 0);
                     }
                     umma_commit(B_EMPTY(s));          // B stage reusable once these MMAs retire
                     umma_commit(ACC_FULL(acc));       // accumulator ready for the epilogue
@@ -638,15 +666,19 @@ static EncodeFn get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap *m, void *base, uint64_t rows, int KP, uint32_t box_rows) {
+// {box_cols bf16, box_rows} boxes starting at any column of a [rows, KP] bf16 matrix; box_cols 64 -> SWIZZLE_128B,
+// 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B (the box's inner extent is exactly the swizzle span)
+static int make_map(CUtensorMap *m, void *base, uint64_t rows, int KP, uint32_t box_cols, uint32_t box_rows) {
     EncodeFn enc = get_encode();
     if (!enc) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)KP * 2};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return EB_OK;
 }
@@ -661,7 +693,8 @@ struct TcLayout {
 // fold = the item bias travels through the MMA as two extra K columns (bf16 hi + lo) against ones on the user side
 static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
     TcLayout L;
-    L.KP = (d + (fold ? 2 : 0) + 63) / 64 * 64;
+    L.KP = (d + (fold ? 2 : 0) + 15) / 16 * 16;          // K padded to the MMA's K = 16 ...
+    if (L.KP % 64 == 48) L.KP += 16;                     // ... except that a 48-column tail becomes a full 64-wide block
     size_t off = 0;
     L.ubf = off; off += al((size_t)n_sel * L.KP * 2);
     L.vbf = off; off += al((size_t)n_items * L.KP * 2);
@@ -676,22 +709,31 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
     return L;
 }
 
-template <int KP, bool DUMP, bool HAS_BIAS>
-static int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    auto kern = score_topk_tc_kernel<KP, DUMP, HAS_BIAS>;
+struct TcMaps { CUtensorMap a, b, at, bt; };
+
+template <int KP, bool HAS_BIAS>
+static int launch_tc3(const TcMaps &m, const TcParams &p, int n_mblocks, cudaStream_t st) {
+    auto kern = score_topk_tc_kernel<KP, HAS_BIAS>;
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP>::SMEM));
     int grid = sm_count();
     if (grid > n_mblocks) grid = n_mblocks;
-    kern<<<grid, TcCfg<KP>::THREADS, TcCfg<KP>::SMEM, st>>>(a, b, p);
+    kern<<<grid, TcCfg<KP>::THREADS, TcCfg<KP>::SMEM, st>>>(m.a, m.b, m.at, m.bt, p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
 
 template <int KP>
-static int launch_tc(const CUtensorMap &a, const CUtensorMap &b, const TcParams &p, int n_mblocks, cudaStream_t st) {
+static int launch_tc(void *ubf, void *vbf, const TcParams &p, int n_mblocks, cudaStream_t st) {
+    using C = TcCfg<KP>;
+    TcMaps m;
+    // a tile without full blocks (KP = 16 / 32) still needs valid descriptors in the unused slots
+    const uint32_t bc = C::KB ? 64 : C::KT, tc = C::KT ? C::KT : 64;
+    if (int rc = make_map(&m.a, ubf, (uint64_t)p.n_sel, KP, bc, TC_BM)) return rc;
+    if (int rc = make_map(&m.b, vbf, (uint64_t)p.n_items, KP, bc, C::BN)) return rc;
+    if (int rc = make_map(&m.at, ubf, (uint64_t)p.n_sel, KP, tc, TC_BM)) return rc;
+    if (int rc = make_map(&m.bt, vbf, (uint64_t)p.n_items, KP, tc, C::BN)) return rc;
     const bool hb = p.bias != nullptr && !p.bias_folded;    // epilogue adds the bias only when it is not folded into the MMA
-    if (p.dump) return hb ? launch_tc3<KP, true, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, true, false>(a, b, p, n_mblocks, st);
-    return hb ? launch_tc3<KP, false, true>(a, b, p, n_mblocks, st) : launch_tc3<KP, false, false>(a, b, p, n_mblocks, st);
+    return hb ? launch_tc3<KP, true>(m, p, n_mblocks, st) : launch_tc3<KP, false>(m, p, n_mblocks, st);
 }
 
 }  // namespace eb
@@ -709,6 +751,12 @@ extern "C" int eb_score_topk_f32_mapped(const float *U, const float *V, const fl
                                         const int32_t *positions, int32_t user_begin, int64_t n_sel, int k,
                                         int32_t *out_idx, float *out_val, void *workspace, size_t workspace_bytes,
                                         void *stream);
+// the same with the number of rows read from device memory at kernel start (n_rows_dev[0] <= n_sel_max)
+extern "C" int eb_score_topk_f32_mapped_dev(const float *U, const float *V, const float *item_bias, int32_t n_items, int d,
+                                            int ld, const int64_t *mask_indptr, const int32_t *mask_indices,
+                                            const int32_t *positions, const int32_t *n_rows_dev, int32_t user_begin,
+                                            int64_t n_sel_max, int k, int32_t *out_idx, float *out_val, void *workspace,
+                                            size_t workspace_bytes, void *stream);
 
 extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
                                     const int64_t *mask_indptr, const int32_t *mask_indices, int32_t user_begin,
@@ -739,10 +787,6 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     tc_convert_kernel<<<cgrid, 256, 0, st>>>(V, n_items, d, ld, 0, vbf, L.KP, nullptr, vstat, fold ? 2 : 0, item_bias);
     if (item_bias) tc_bias_kernel<<<((n_items + 31) / 32 + 255) / 256, 256, 0, st>>>(item_bias, n_items, bmax, vstat + 1);
     EB_CUDA(cudaGetLastError());
-    CUtensorMap ma, mb;
-    const int BN = L.KP <= 128 ? 256 : (L.KP == 192 ? 128 : 64);     // must equal TcCfg<KP>::BN
-    if (int rc = make_map(&ma, ubf, (uint64_t)n_sel, L.KP, TC_BM)) return rc;
-    if (int rc = make_map(&mb, vbf, (uint64_t)n_items, L.KP, BN)) return rc;
     TcParams p{};
     p.U = U; p.V = V; p.bias = item_bias; p.d = d; p.ld = ld; p.n_items = n_items;
     p.mask_indptr = mask_indptr; p.mask_indices = mask_indices; p.user_begin = user_begin; p.n_sel = (int32_t)n_sel; p.k = k;
@@ -755,24 +799,24 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     const int n_mblocks = (int)((n_sel + TC_BM - 1) / TC_BM);
     int rc;
     switch (L.KP) {
-        case 64: rc = launch_tc<64>(ma, mb, p, n_mblocks, st); break;
-        case 128: rc = launch_tc<128>(ma, mb, p, n_mblocks, st); break;
-        case 192: rc = launch_tc<192>(ma, mb, p, n_mblocks, st); break;
-        default: rc = launch_tc<256>(ma, mb, p, n_mblocks, st); break;
+#define EB_TC_CASE(K) case K: rc = launch_tc<K>(ubf, vbf, p, n_mblocks, st); break;
+        EB_TC_CASE(16) EB_TC_CASE(32) EB_TC_CASE(64) EB_TC_CASE(80) EB_TC_CASE(96) EB_TC_CASE(128) EB_TC_CASE(144)
+        EB_TC_CASE(160) EB_TC_CASE(192) EB_TC_CASE(208) EB_TC_CASE(224) EB_TC_CASE(256)
+#undef EB_TC_CASE
+        default: return set_err(EB_ERR_ARG, "internal: unsupported padded K %d", L.KP);
     }
     if (rc) return rc;
-    int32_t flagged = 0;
-    EB_CUDA(cudaMemcpyAsync(&flagged, flag_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    EB_CUDA(cudaStreamSynchronize(st));
-    if (stats_host) {
+    // provably-exact re-check of the users the bound could not certify: launched unconditionally over the DEVICE-side
+    // count (no host round trip per call; with nothing flagged the CTAs exit at once)
+    rc = eb_score_topk_f32_mapped_dev(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, flag_list, flag_count, user_begin,
+                                      n_sel, k, out_idx, out_val, ws + L.exact_ws, L.exact_bytes, stream);
+    if (rc) return rc;
+    if (stats_host) {                                   // statistics are the only reason to synchronise
+        int32_t flagged = 0;
+        EB_CUDA(cudaMemcpyAsync(&flagged, flag_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EB_CUDA(cudaStreamSynchronize(st));
         stats_host[0] = flagged; stats_host[1] = L.KP;
         if (p.prof) EB_CUDA(cudaMemcpy(stats_host + 2, p.prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
-    }
-    if (flagged > 0) {
-        // provably-exact re-check of the users the bound could not certify
-        rc = eb_score_topk_f32_mapped(U, V, item_bias, n_items, d, ld, mask_indptr, mask_indices, flag_list, user_begin,
-                                      flagged, k, out_idx, out_val, ws + L.exact_ws, L.exact_bytes, stream);
-        if (rc) return rc;
     }
     return EB_OK;
 }

@@ -187,10 +187,11 @@ def score_topk(U, V, bias, d, k, mask_indptr=None, mask_indices=None, users=None
 _ws_tc = _Workspace()
 
 
-def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_begin=0, n_sel=None, dump=False):
+def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_begin=0, n_sel=None, dump=False, stats=True):
     """Tensor-core scoring + top-k (fp32 tables); same result as score_topk().  Returns
     (idx, val, stats) with stats = {"rechecked": users re-done by the exact kernel, "kp": padded K}
-    (+ "dump": dense approximate scores when dump=True, tests only)."""
+    (+ "dump": dense approximate scores when dump=True, tests only).  stats=False: nothing is read back, the call
+    stays asynchronous (the models' path) and the dict is empty."""
     _need_cuda(U, V, bias, mask_indptr, mask_indices)
     assert U.dtype == torch.float32 and V.dtype == torch.float32 and U.stride(0) == V.stride(0)
     if n_sel is None:
@@ -201,12 +202,12 @@ def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_be
     val = torch.empty((n_sel, k), dtype=torch.float32, device=dev)
     dmp = torch.zeros((n_sel, n_items), dtype=torch.float32, device=dev) if dump else None
     ws = _ws_tc.get(lib().eb_score_topk_tc_workspace_bytes(n_sel, n_items, d), dev)
-    stats = (ctypes.c_int64 * 16)()
+    st = (ctypes.c_int64 * 16)() if stats else None
     with torch.cuda.device(dev):
         check(lib().eb_score_topk_tc_f32(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr),
                                          _ptr(mask_indices), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(dmp),
-                                         _ptr(ws), ws.numel(), ctypes.cast(stats, ctypes.c_void_p), _stream(U)))
-    out = {"rechecked": int(stats[0]), "kp": int(stats[1]), "prof": [int(x) for x in stats[2:10]]}
+                                         _ptr(ws), ws.numel(), ctypes.cast(st, ctypes.c_void_p) if stats else None, _stream(U)))
+    out = {"rechecked": int(st[0]), "kp": int(st[1]), "prof": [int(x) for x in st[2:10]]} if stats else {}
     if dump:
         out["dump"] = dmp
     return idx, val, out

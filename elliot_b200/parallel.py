@@ -85,6 +85,16 @@ class GradAllReduce:
             dist.all_reduce(self.extra, group=self.group)
         return world
 
+    def sync_weighted(self, local_rows, global_rows):
+        """The same for slices of UNEQUAL size (the tail batch of an epoch; a rank may even hold no row at all and then
+        contributes the zero gradient): every rank's gradient is a mean over ITS rows, the global-batch gradient is
+        sum_r (B_r / B) g_r = mean_r (world B_r / B) g_r, so each rank pre-scales and the usual average follows.
+        Every rank must call it, whatever its slice."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1 and int(global_rows) != int(local_rows) * world:
+            self.flat.mul_(world * float(local_rows) / float(global_rows))
+        return self.sync()
+
 
 class OverlappedTableSync:
     """Same reconciliation, one step late, so the all-reduce of step k overlaps the compute of step k+1

@@ -81,7 +81,7 @@ class MFModel:
     # ---- scoring (BPRMF_model.py:70-85) ----------------------------------------------------
     def topk(self, k, mask_indptr, mask_indices, users=None):
         if self._mode != "exact" and users is None and k <= 16:          # fp32 tables: tensor-core path, same result
-            idx, val, _ = ops.score_topk_tc(self.U, self.V, self.b, self._factors, k, mask_indptr, mask_indices)
+            idx, val, _ = ops.score_topk_tc(self.U, self.V, self.b, self._factors, k, mask_indptr, mask_indices, stats=False)
             return idx, val
         return ops.score_topk(self.U, self.V, self.b, self._factors, k, mask_indptr, mask_indices, users=users)
 

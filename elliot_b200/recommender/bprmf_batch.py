@@ -57,9 +57,9 @@ class BPRMFBatchModel:
     def topk(self, k, mask_indptr, mask_indices, tensor_cores=True):
         bias = self.Bi[:self._num_items]
         if tensor_cores and k <= 16:
-            idx, val, _ = ops.score_topk_tc(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices)
+            idx, val, _ = ops.score_topk_tc(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices, stats=False)
             return idx, val
-        return ops.score_topk(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices)
+        return ops.score_topk(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices, stats=False)
 
     def get_model_state(self):
         F = self._factors

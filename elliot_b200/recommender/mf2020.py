@@ -90,9 +90,9 @@ class MF2020Model:
         """Scores gb + ub[u] + ib[i] + U[u].V[i] (MF_model.py:113-114); the per-user constant does not change the
         ranking, so the kernels rank ib + U.V and the constant is added to the returned values."""
         if self._mode != "exact" and k <= 16:
-            idx, val, _ = ops.score_topk_tc(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices)
+            idx, val, _ = ops.score_topk_tc(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices, stats=False)
         else:
-            idx, val = ops.score_topk(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices)
+            idx, val = ops.score_topk(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices, stats=False)
         return idx, val + (self.ub + self.gb).to(val.dtype).unsqueeze(1)
 
     def load_weights(self, path):

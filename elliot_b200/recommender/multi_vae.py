@@ -104,16 +104,25 @@ class VariationalAutoEncoder:
         logits = ops.gemm_bf16_tn(ops.to_bf16(h2), self.W4b, B, I, H, bias=self.P["b4"])
         return h1, ml, z, h2, logits
 
-    def train_step(self, rows, anneal):
-        """rows: int32 device tensor of private user ids.  Returns the loss as a python float."""
+    def train_step(self, rows, anneal, global_batch=None):
+        """rows: int32 device tensor of private user ids (data parallel: THIS rank's slice, possibly empty).
+        global_batch: number of rows of the whole batch over all ranks (default: world x this slice).
+        Returns the loss as a python float — the same value on every rank."""
         B, L = rows.numel(), self.L
         self.step += 1
         self._acc.zero_()
-        self.compute_grads(rows, anneal, self.step)
-        world = self.dp.sync() if self.dp is not None else 1     # data parallel: average grads, sum the loss terms
+        if B > 0:
+            self.compute_grads(rows, anneal, self.step)      # B == 0: the gradient buffer is already zero (Adam clears it)
+        world = 1
+        if self.dp is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.dp.group) if dist.is_initialized() else 1
+            Bg = int(global_batch) if global_batch is not None else B * world
+            self.dp.sync_weighted(B, Bg)                         # global-batch gradient (slices may be unequal or empty), loss terms summed
+        else:
+            Bg = B
         self.apply_grads()
         kl_sum, nll_sum = self._acc.tolist()
-        Bg = B * world                                           # equal slices (the caller splits evenly, +-1 row)
         return nll_sum / Bg + anneal * (-0.5 * kl_sum / (Bg * L))
 
     def compute_grads(self, rows, anneal, sid):
@@ -242,14 +251,15 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
             order = torch.tensor(order, dtype=torch.int32, device=self._device)
             for s in range(0, self._num_users, self._batch_size):
                 rows = order[s:s + self._batch_size].contiguous()
-                if self._dp:                                     # this rank's slice of the batch (sizes differ by <= 1)
-                    import torch.distributed as dist
+                n_batch = rows.numel()
+                if self._dp:                                     # this rank's slice of the batch: sizes differ by <= 1, and a
+                    import torch.distributed as dist             # tail batch smaller than the world leaves some ranks EMPTY
                     from ..parallel import shard_range
-                    lo, hi = shard_range(rows.numel(), dist.get_rank(), dist.get_world_size())
+                    lo, hi = shard_range(n_batch, dist.get_rank(), dist.get_world_size())
                     rows = rows[lo:hi].contiguous()
                 anneal = min(self._anneal_cap, 1. * self._update_count / self._total_anneal_steps) \
                     if self._total_anneal_steps > 0 else self._anneal_cap
-                loss += self._model.train_step(rows, anneal)
+                loss += self._model.train_step(rows, anneal, global_batch=n_batch)
                 self._update_count += 1
             self.evaluate(it, loss / (it + 1))
 

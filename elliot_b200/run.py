@@ -140,7 +140,9 @@ def run_experiment(config_path: str = ""):
             fold_results.append({"loss": model.get_loss(), "params": {k: v for k, v in model.get_params().items() if k != "meta"},
                                  "val_results": {k: res[k]["val_results"] for k in res},
                                  "test_results": {k: res[k]["test_results"] for k in res},
-                                 "name": model.name})
+                                 "name": model.name,
+                                 # every evaluated epoch's test metrics (the reference only logs them)
+                                 "history": [{k: r[k]["test_results"] for k in r} for r in model._results]})
         best = min(fold_results, key=lambda r: r["loss"])
         all_results.append(best)
     # performance table (result_handler.py:40-81 layout: one row per model, one column per metric)

@@ -383,7 +383,9 @@ int eb_gather_rows_peer_f32(float *const *shards, int n_shards, int32_t shard_ro
  * dump (optional, tests): dense n_sel x n_items raw approximate scores.
  * stats_host (optional, host int64[16]): [0] users re-done exactly, [1] padded K, [2..9] cycle
  * counters of CTA 0 when the environment variable EB_TC_PROF is set (profiling aid).
- * Synchronises the stream once (to read the re-check count). */
+ * Asynchronous unless stats_host is given (reading the statistics back is the only synchronisation): the exact
+ * re-check runs over a device-side count.  K is padded to a multiple of 16 (full 64-column blocks with the 128-byte
+ * swizzle plus one 16- or 32-column tail block with the 32-/64-byte swizzle), not to a multiple of 64. */
 size_t eb_score_topk_tc_workspace_bytes(int64_t n_sel, int32_t n_items, int d);
 int eb_score_topk_tc_f32(const float *U, const float *V, const float *item_bias, int32_t n_items, int d, int ld,
                          const int64_t *mask_indptr, const int32_t *mask_indices,

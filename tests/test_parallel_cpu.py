@@ -119,6 +119,15 @@ def _worker(rank, world, init_file, out_dir):
     w = GradAllReduce(gflat, extra=acc).sync()
     ok = ok and w == world and torch.allclose(gflat, torch.arange(6, dtype=torch.float32) * sum(r + 1 for r in range(world)) / world) \
         and torch.equal(acc, torch.tensor([sum(1.0 + r for r in range(world)), 10.0 * world], dtype=torch.float64))
+    # unequal and EMPTY slices (tail batch of an epoch): mean-over-own-rows gradients combined into the
+    # global-batch mean; a rank without rows contributes zeros and still takes part
+    X = torch.arange(12, dtype=torch.float32).reshape(3, 4) + 1.0           # 3 rows over 2 ranks: slices of 2 and 1
+    for n_rows in (3, 1):                                                     # n_rows = 1: rank 1 is empty
+        lo_r, hi_r = shard_range(n_rows, rank, world)
+        mine = X[lo_r:hi_r]
+        g = mine.mean(0).clone() if hi_r > lo_r else torch.zeros(4)
+        GradAllReduce(g).sync_weighted(hi_r - lo_r, n_rows)
+        ok = ok and torch.allclose(g, X[:n_rows].mean(0), atol=1e-6)
     torch.save({"ok": ok, "V": V}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
