@@ -22,6 +22,12 @@ SIGNATURES = {
     "eb_bpr_step_sampled_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i32, c_i32, c_void, c_void,
                                         c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32,
                                         c_void, c_void, c_void, c_void, c_int, c_void]),
+    "eb_bloom_build": (c_int, [c_void, c_void, c_i32, c_int, c_void, c_void]),
+    "eb_bpr_step_sampled_filter_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i32, c_i32, c_void, c_void, c_void, c_int,
+                                               c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32,
+                                               c_void, c_void, c_void, c_void, c_int, c_void]),
+    "eb_bpr_sample_philox_filter": (c_int, [c_i32, c_i32, c_void, c_void, c_void, c_int, c_i64, c_u64, c_u64, c_void, c_void, c_void,
+                                            c_void]),
     "eb_bpr_sample_philox": (c_int, [c_i32, c_i32, c_void, c_void, c_i64, c_u64, c_u64, c_void, c_void, c_void,
                                      c_void]),
     "eb_bpr_step_host_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
@@ -90,7 +96,7 @@ SIGNATURES = {
     "eb_bpr_step_peer_f32": (c_int, [c_void, c_void, c_void, c_int, c_i32, c_int, c_int, c_i32, c_void, c_void, c_void, c_i64,
                                      c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_int, c_void]),
     "eb_bpr_step_sampled_peer_f32": (c_int, [c_void, c_void, c_void, c_int, c_i32, c_int, c_int, c_i32, c_i32, c_void, c_void,
-                                             c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void,
+                                             c_void, c_int, c_i64, c_u64, c_u64, c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void,
                                              c_void, c_int, c_void]),
     "eb_table_reconcile_peer_f32": (c_int, [c_void, c_int, c_void, c_i64, c_f32, c_int, c_void]),
     "eb_neumf_gather_peer": (c_int, [c_void, c_void, c_i64, c_void, c_int, c_i32, c_i64, c_int, c_void, c_void, c_i64, c_void,

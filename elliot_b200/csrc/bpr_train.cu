@@ -38,6 +38,9 @@ struct HogwildParams {
     // (cudaIpcOpenMemHandle, peer.cu) for the others; loads and vector atomics go straight over NVLink.
     float *Vp[EB_MAX_PEERS], *bp[EB_MAX_PEERS];
     uint32_t shard_rows, shard_magic;          // magic = floor(2^32 / shard_rows)
+    // optional per-user membership signatures (eb_bloom_build): filter_log2bits bits per user
+    const uint32_t *filter;
+    int filter_log2bits;
 };
 
 // owner shard and row inside it (one multiply-high and one correction instead of an integer division)
@@ -59,21 +62,36 @@ __device__ __forceinline__ void sample_triple(const HogwildParams &p, int64_t t,
     int64_t beg = __ldg(p.indptr + u), end = __ldg(p.indptr + u + 1);
     int len = (int)(end - beg);
     uint32_t attempt = 0;
-    while (len == 0) {  // users without train items never appear in the reference's dict
+    while (len == 0 || len >= p.n_items) {  // users without train items never appear in the reference's dict; a user owning
+                                            // every item has no negative at all (the reference would loop forever)
         Philox::gen(p.seed, p.first + (uint64_t)t, ++attempt | 0x80000000u, r);
         u = (int)bounded(r[0], (uint32_t)p.n_users);
         beg = __ldg(p.indptr + u); end = __ldg(p.indptr + u + 1); len = (int)(end - beg);
     }
     const int32_t *row = p.indices + beg;
-    i = __ldg(row + bounded(r[1], (uint32_t)len));
     int cand = (int)bounded(r[2], (uint32_t)p.n_items);
-    if (!contains_sorted(row, len, cand)) { j = cand; return; }
+    // the signature words depend on u only: their loads are in flight together with the pick of i
+    const bool maybe = p.filter ? bloom_maybe(p.filter + ((int64_t)u << (p.filter_log2bits - 5)), p.filter_log2bits, (uint32_t)cand) : true;
+    i = __ldg(row + bounded(r[1], (uint32_t)len));
+    if (!maybe || !contains_sorted(row, len, cand)) { j = cand; return; }
     cand = (int)bounded(r[3], (uint32_t)p.n_items);
     attempt = 0;
     int q = 4;
-    while (contains_sorted(row, len, cand) && attempt < 4096u) {
+    while (contains_sorted(row, len, cand) && attempt < 16u) {
         if (q == 4) { Philox::gen(p.seed, p.first + (uint64_t)t, ++attempt, r); q = 0; }
         cand = (int)bounded(r[q++], (uint32_t)p.n_items);
+    }
+    if (attempt >= 16u && contains_sorted(row, len, cand)) {
+        // near-dense user: stop rejecting and draw the rank-th item of the complement directly (same uniform
+        // distribution over the non-train items, never a train item): smallest pos with row[pos] - pos > rank
+        Philox::gen(p.seed, p.first + (uint64_t)t, 0x40000000u, r);          // a fresh block: independent of the rejected candidates
+        const uint32_t rank = bounded(r[0], (uint32_t)(p.n_items - len));
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)(__ldg(row + mid) - mid) > rank) hi = mid; else lo = mid + 1;
+        }
+        cand = (int)rank + lo;
     }
     j = cand;
 }
@@ -134,6 +152,15 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                 if (p.out_u) { p.out_u[t] = u; p.out_i[t] = i; p.out_j[t] = j; }
             } else {
                 u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
+            }
+            if (!PEER) {
+                // the rows are consumed up to 8 rounds later (the groups walk the warp's 32 triples): pull them into
+                // L2 now so that those loads pay L2 instead of HBM latency
+                const char *ru = reinterpret_cast<const char *>(p.U + (int64_t)u * ld);
+                const char *ri = reinterpret_cast<const char *>(p.V + (int64_t)i * ld);
+                const char *rj = reinterpret_cast<const char *>(p.V + (int64_t)j * ld);
+#pragma unroll
+                for (int b = 0; b < DP * 4; b += 128) { prefetch_l2(ru + b); prefetch_l2(ri + b); prefetch_l2(rj + b); }
             }
         }
         // UNR triples of the group in flight at once: all their row loads are issued before the first reduction
@@ -219,6 +246,28 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
         if (lane == 0 && loss_acc != 0.f) atomicAdd(p.loss, (double)loss_acc);
+    }
+}
+
+// one warp per user: OR the two signature bits of every train item into the user's words
+__global__ void __launch_bounds__(256) bloom_build_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                          int32_t n_users, int log2bits, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int words = 1 << (log2bits - 5);
+    for (; w < n_users; w += nw) {
+        uint32_t *f = out + w * words;
+        for (int k = lane; k < words; k += 32) f[k] = 0u;
+        __syncwarp();
+        const int64_t beg = indptr[w], end = indptr[w + 1];
+        for (int64_t e = beg + lane; e < end; e += 32) {
+            uint32_t a, b;
+            bloom_bits((uint32_t)indices[e], log2bits, a, b);
+            atomicOr(f + (a >> 5), 1u << (a & 31));
+            atomicOr(f + (b >> 5), 1u << (b & 31));
+        }
+        __syncwarp();
     }
 }
 
@@ -467,11 +516,44 @@ extern "C" int eb_bpr_step_f32(float *U, float *V, float *item_bias, int d, int 
     return launch_hogwild<false>(p, ld, flags, (cudaStream_t)stream);
 }
 
+static int set_filter(HogwildParams &p, const uint32_t *filter, int filter_words) {
+    if (!filter) return EB_OK;
+    EB_ARG(filter_words >= 1 && filter_words <= 1024 && (filter_words & (filter_words - 1)) == 0,
+           "filter_words must be a power of two in [1, 1024] (got %d)", filter_words);
+    int lb = 5;
+    while ((1 << (lb - 5)) < filter_words) lb++;
+    p.filter = filter; p.filter_log2bits = lb;
+    return EB_OK;
+}
+
+extern "C" int eb_bloom_build(const int64_t *csr_indptr, const int32_t *csr_indices, int32_t n_users, int filter_words,
+                              uint32_t *out, void *stream) {
+    EB_ARG(csr_indptr && csr_indices && out && n_users >= 1, "bad argument");
+    HogwildParams p{};
+    if (int rc = set_filter(p, out, filter_words)) return rc;
+    int64_t grid = ((int64_t)n_users * 32 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    bloom_build_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(csr_indptr, csr_indices, n_users, p.filter_log2bits, out);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
 extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int d, int ld, int32_t n_users,
                                        int32_t n_items, const int64_t *csr_indptr, const int32_t *csr_indices,
                                        int64_t n, uint64_t seed, uint64_t first_triple, float lr, float reg_u,
                                        float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
                                        int32_t *out_i, int32_t *out_j, int flags, void *stream) {
+    return eb_bpr_step_sampled_filter_f32(U, V, item_bias, d, ld, n_users, n_items, csr_indptr, csr_indices, nullptr, 0, n, seed,
+                                          first_triple, lr, reg_u, reg_b, reg_pos, reg_neg, loss, out_u, out_i, out_j, flags, stream);
+}
+
+extern "C" int eb_bpr_step_sampled_filter_f32(float *U, float *V, float *item_bias, int d, int ld, int32_t n_users,
+                                              int32_t n_items, const int64_t *csr_indptr, const int32_t *csr_indices,
+                                              const uint32_t *filter, int filter_words, int64_t n, uint64_t seed,
+                                              uint64_t first_triple, float lr, float reg_u, float reg_b, float reg_pos,
+                                              float reg_neg, double *loss, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                                              int flags, void *stream) {
     if (int rc = check_tables(U, V, item_bias, d, ld)) return rc;
     EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
     EB_ARG(csr_indptr && csr_indices, "null CSR");
@@ -482,6 +564,7 @@ extern "C" int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    if (int rc = set_filter(p, filter, filter_words)) return rc;
     return launch_hogwild<true>(p, ld, flags, (cudaStream_t)stream);
 }
 
@@ -502,7 +585,8 @@ extern "C" int eb_bpr_step_peer_f32(float *U, float *const *V_shards, float *con
 
 extern "C" int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
                                             int d, int ld, int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
-                                            const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple, float lr,
+                                            const int32_t *csr_indices, const uint32_t *filter, int filter_words, int64_t n,
+                                            uint64_t seed, uint64_t first_triple, float lr,
                                             float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
                                             int32_t *out_i, int32_t *out_j, int flags, void *stream) {
     EB_ARG(U && d >= 1 && ld >= d && ((uintptr_t)U % 16) == 0, "bad user table");
@@ -516,18 +600,28 @@ extern "C" int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, fl
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    if (int rc = set_filter(p, filter, filter_words)) return rc;
     return launch_hogwild_peer<true>(p, ld, flags, (cudaStream_t)stream);
 }
 
 extern "C" int eb_bpr_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
                                     const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple,
                                     int32_t *out_u, int32_t *out_i, int32_t *out_j, void *stream) {
+    return eb_bpr_sample_philox_filter(n_users, n_items, csr_indptr, csr_indices, nullptr, 0, n, seed, first_triple, out_u, out_i,
+                                       out_j, stream);
+}
+
+extern "C" int eb_bpr_sample_philox_filter(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
+                                           const int32_t *csr_indices, const uint32_t *filter, int filter_words, int64_t n,
+                                           uint64_t seed, uint64_t first_triple, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                                           void *stream) {
     EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
     EB_ARG(csr_indptr && csr_indices && out_u && out_i && out_j, "null pointer");
     if (n == 0) return EB_OK;
     HogwildParams p{};
     p.n = n; p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    if (int rc = set_filter(p, filter, filter_words)) return rc;
     int64_t grid = (n + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;

@@ -71,6 +71,20 @@ __device__ static inline bool contains_sorted(const int32_t *__restrict__ a, int
     return lo < len && __ldg(a + lo) == key;
 }
 
+// Per-user membership signature (a Bloom filter of 32*words bits, 2 hashes) over the user's train items: the sampler's
+// rejection test `j in ui` (custom_sampler.py:40-41) is a MISS for all but ~len/n_items of the candidates, and a miss is
+// proven by one or two word loads here instead of a dependent binary search over the CSR row.  words is a power of two.
+__host__ __device__ static inline void bloom_bits(uint32_t x, int log2bits, uint32_t &a, uint32_t &b) {
+    a = (x * 0x9E3779B1u) >> (32 - log2bits);
+    b = ((x ^ 0x5bd1e995u) * 0x85EBCA6Bu) >> (32 - log2bits);
+}
+__device__ static inline bool bloom_maybe(const uint32_t *__restrict__ f, int log2bits, uint32_t x) {
+    uint32_t a, b;
+    bloom_bits(x, log2bits, a, b);
+    return ((__ldg(f + (a >> 5)) >> (a & 31)) & (__ldg(f + (b >> 5)) >> (b & 31)) & 1u) != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 128-bit / 32-bit fire-and-forget float adds (REDG.E.ADD.F32x4 / REDG.E.ADD.F32 on sm_100a)
 __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),

@@ -29,7 +29,6 @@ struct MfSeqParams {
     double *batch_loss;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NE>
 __global__ void __launch_bounds__(32) mf_pointwise_seq_kernel(const MfSeqParams p) {

@@ -60,29 +60,41 @@ def bpr_step_f32(U, V, b, d, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, los
                                     lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), 1 if racy else 0, _stream(U)))
 
 
+def bloom_build(indptr, indices, n_users, words=32):
+    """Per-user membership signatures for the fused sampler (32*words bits each, see eb_bloom_build): uint32 [n_users, words]
+    (kept as int32 storage).  With them the sampler draws EXACTLY the same triples, just with a shorter load chain."""
+    _need_cuda(indptr, indices)
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+    out = torch.empty((n_users, words), dtype=torch.int32, device=indptr.device)
+    with torch.cuda.device(indptr.device):
+        check(lib().eb_bloom_build(_ptr(indptr), _ptr(indices), n_users, words, _ptr(out), _stream(indptr)))
+    return out
+
+
 def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u, reg_b, reg_pos,
-                         reg_neg, loss=None, out=None, racy=False, reserve_sms=0):
-    """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream)."""
-    _need_cuda(U, V, b, indptr, indices, loss)
+                         reg_neg, loss=None, out=None, racy=False, reserve_sms=0, filter=None):
+    """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream).  filter: bloom_build() output."""
+    _need_cuda(U, V, b, indptr, indices, loss, filter)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     ou = oi = oj = None
     if out is not None:
         ou, oi, oj = out
         _need_cuda(ou, oi, oj); _chk_idx(ou, oi, oj)
     with torch.cuda.device(U.device):
-        check(lib().eb_bpr_step_sampled_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), n_users, n_items, _ptr(indptr),
-                                            _ptr(indices), n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg,
-                                            _ptr(loss), _ptr(ou), _ptr(oi), _ptr(oj),
-                                            (1 if racy else 0) | ((int(reserve_sms) & 0xff) << 8), _stream(U)))
+        check(lib().eb_bpr_step_sampled_filter_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), n_users, n_items, _ptr(indptr),
+                                                   _ptr(indices), _ptr(filter), 0 if filter is None else filter.shape[1], n, seed,
+                                                   first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), _ptr(ou), _ptr(oi),
+                                                   _ptr(oj), (1 if racy else 0) | ((int(reserve_sms) & 0xff) << 8), _stream(U)))
 
 
-def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0):
-    _need_cuda(indptr, indices)
+def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0, filter=None):
+    _need_cuda(indptr, indices, filter)
     dev = indptr.device
     u = torch.empty(n, dtype=torch.int32, device=dev); i = torch.empty_like(u); j = torch.empty_like(u)
     with torch.cuda.device(dev):
-        check(lib().eb_bpr_sample_philox(n_users, n_items, _ptr(indptr), _ptr(indices), n, seed, first, _ptr(u),
-                                         _ptr(i), _ptr(j), _stream(indptr)))
+        check(lib().eb_bpr_sample_philox_filter(n_users, n_items, _ptr(indptr), _ptr(indices), _ptr(filter),
+                                                0 if filter is None else filter.shape[1], n, seed, first, _ptr(u), _ptr(i), _ptr(j),
+                                                _stream(indptr)))
     return u, i, j
 
 
@@ -571,7 +583,7 @@ def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj,
 
 
 def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u,
-                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0):
+                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0, filter=None):
     """Fused sample+update step with the item table row-sharded over the GPUs of the box (loads / atomics over NVLink)."""
     _need_cuda(U, indptr, indices, loss)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and U.dtype == torch.float32 and U.stride(1) == 1
@@ -583,7 +595,7 @@ def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_i
         _need_cuda(ou, oi, oj); _chk_idx(ou, oi, oj)
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_sampled_peer_f32(_ptr(U), va, ba, ns, shard_rows, d, U.stride(0), n_users, n_items, _ptr(indptr),
-                                                 _ptr(indices), n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss),
+                                                 _ptr(indices), _ptr(filter), 0 if filter is None else filter.shape[1], n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss),
                                                  _ptr(ou), _ptr(oi), _ptr(oj), (int(reserve_sms) & 0xff) << 8, _stream(U)))
 
 

@@ -77,6 +77,27 @@ int eb_bpr_step_sampled_f32(float *U, float *V, float *item_bias, int d, int ld,
                             double *loss, int32_t *out_u, int32_t *out_i, int32_t *out_j,
                             int flags, void *stream);
 
+/* Per-user membership signatures for the sampler's rejection test (`j in ui`, custom_sampler.py:40-41): a Bloom
+ * filter of 32*filter_words bits (filter_words a power of two, 32 = 1024 bits suits ~100 items/user) with 2 hash
+ * functions per user, out[u*filter_words ...].  A candidate the signature rules out is accepted without touching the
+ * CSR row; only "maybe" answers run the binary search, so the samples are EXACTLY those of the unfiltered sampler
+ * (same stream, same triples) — only the dependent-load chain gets shorter. */
+int eb_bloom_build(const int64_t *csr_indptr, const int32_t *csr_indices, int32_t n_users, int filter_words,
+                   uint32_t *out, void *stream);
+/* eb_bpr_step_sampled_f32 with the signatures (filter may be NULL) */
+int eb_bpr_step_sampled_filter_f32(float *U, float *V, float *item_bias, int d, int ld,
+                                   int32_t n_users, int32_t n_items,
+                                   const int64_t *csr_indptr, const int32_t *csr_indices,
+                                   const uint32_t *filter, int filter_words,
+                                   int64_t n, uint64_t seed, uint64_t first_triple,
+                                   float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
+                                   double *loss, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                                   int flags, void *stream);
+int eb_bpr_sample_philox_filter(int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
+                                const int32_t *csr_indices, const uint32_t *filter, int filter_words, int64_t n,
+                                uint64_t seed, uint64_t first_triple, int32_t *out_u, int32_t *out_i, int32_t *out_j,
+                                void *stream);
+
 /* Sample only (no update): same sampler as above, for tests and for host
  * pipelines that want materialised triples. */
 int eb_bpr_sample_philox(int32_t n_users, int32_t n_items,
@@ -347,7 +368,8 @@ int eb_bpr_step_peer_f32(float *U, float *const *V_shards, float *const *b_shard
                          void *stream);
 int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, float *const *b_shards, int n_shards, int32_t shard_rows,
                                  int d, int ld, int32_t n_users, int32_t n_items, const int64_t *csr_indptr,
-                                 const int32_t *csr_indices, int64_t n, uint64_t seed, uint64_t first_triple, float lr,
+                                 const int32_t *csr_indices, const uint32_t *filter, int filter_words, int64_t n,
+                                 uint64_t seed, uint64_t first_triple, float lr,
                                  float reg_u, float reg_b, float reg_pos, float reg_neg, double *loss, int32_t *out_u,
                                  int32_t *out_i, int32_t *out_j, int flags, void *stream);
 

@@ -203,6 +203,51 @@ def test_philox_sampler_invariants(golden_small):
     assert abs(chi2 - (len(r2) - 1)) < 6 * np.sqrt(2 * (len(r2) - 1))
 
 
+@pytest.mark.parametrize("words", [1, 8, 32])
+def test_membership_signatures_do_not_change_the_samples(golden_small, words):
+    """The Bloom signatures only prove misses: with them the sampler emits exactly the unfiltered sampler's triples."""
+    g = golden_small
+    nu, ni = len(g["users"]), len(g["items"])
+    indptr, _, srt = _csr_dev(g)
+    filt = ops.bloom_build(indptr, srt, nu, words)
+    # every train item sets both of its bits (host recomputation of the two hash positions)
+    f = filt.cpu().numpy().view(np.uint32)
+    lb = 5 + int(np.log2(words))
+    for u in (0, 2, nu - 1):
+        for x in g["ui_indices"][g["ui_indptr"][u]:g["ui_indptr"][u + 1]].astype(np.uint32):
+            a = (int(x) * 0x9E3779B1 & 0xFFFFFFFF) >> (32 - lb)
+            bb = ((int(x) ^ 0x5bd1e995) * 0x85EBCA6B & 0xFFFFFFFF) >> (32 - lb)
+            assert (f[u, a >> 5] >> (a & 31)) & 1 and (f[u, bb >> 5] >> (bb & 31)) & 1
+    n = 100000
+    a = ops.bpr_sample_philox(nu, ni, indptr, srt, n, seed=77, first=5)
+    b = ops.bpr_sample_philox(nu, ni, indptr, srt, n, seed=77, first=5, filter=filt)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    d = int(g["d"]); ld = ops.padded_dim(d)
+    hp = [float(x) for x in g["hp"]]
+    out = [torch.empty(4096, dtype=torch.int32, device=DEV) for _ in range(3)]
+    Ud, Vd = _pad(g["U0"], ld, np.float32), _pad(g["V0"], ld, np.float32)
+    ops.bpr_step_sampled_f32(Ud, Vd, torch.zeros(ni, device=DEV), d, nu, ni, indptr, srt, 4096, 77, 5, *hp, out=out, filter=filt)
+    for x, y in zip(out, a):
+        assert torch.equal(x, y[:4096])
+
+
+def test_sampler_near_dense_and_full_users():
+    """A user owning all but 3 items still gets a uniform negative from exactly those 3 (rank draw after the rejection
+    cap); a user owning EVERY item is never sampled (the reference would loop forever on it)."""
+    ni = 64
+    rows = [list(range(ni)), [x for x in range(ni) if x not in (5, 17, 40)], [1, 2, 3]]
+    indptr = torch.tensor(np.cumsum([0] + [len(r) for r in rows]), dtype=torch.int64, device=DEV)
+    idx = torch.tensor([x for r in rows for x in r], dtype=torch.int32, device=DEV)
+    u, i, j = (t.cpu().numpy() for t in ops.bpr_sample_philox(3, ni, indptr, idx, 60000, seed=3))
+    assert set(np.unique(u)) == {1, 2}
+    ju = j[u == 1]
+    assert set(np.unique(ju)) == {5, 17, 40}
+    cnt = np.array([(ju == x).sum() for x in (5, 17, 40)])
+    assert np.all(np.abs(cnt - len(ju) / 3) < 6 * np.sqrt(len(ju) * 2 / 9))
+    assert not np.isin(j[u == 2], [1, 2, 3]).any()
+
+
 def test_fused_sampled_step_equals_sample_then_step(golden_small):
     """The fused kernel's emitted triples equal the stand-alone sampler's, and applying them
     through the materialised-triple kernel on a conflict-free subset gives the same tables."""
