@@ -447,9 +447,14 @@ __global__ void __launch_bounds__(128) bpr_exact_kernel(const ExactParams p) {
 
 // keys: (row << ebits) | event ; events of table `which`: users -> event = t, items -> event = 2t+slot
 __global__ void make_keys_kernel(const int32_t *tu, const int32_t *ti, const int32_t *tj, int64_t n, int ebits,
-                                 uint64_t *keysU, uint64_t *keysI) {
+                                 uint64_t *keysU, uint64_t *keysI, int32_t n_users, int32_t n_items, int32_t *status) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    // a triple with i == j would wait on the same row counter twice (the turn never comes: the kernel would spin for
+    // ever), an id out of range would touch foreign memory: report both before the ordered kernel is launched
+    const uint32_t uu = (uint32_t)tu[t], ii = (uint32_t)ti[t], jj = (uint32_t)tj[t];
+    if (ii == jj) atomicOr(status, 1);
+    if (uu >= (uint32_t)n_users || ii >= (uint32_t)n_items || jj >= (uint32_t)n_items) { atomicOr(status, 2); return; }
     keysU[t] = ((uint64_t)(uint32_t)tu[t] << ebits) | (uint64_t)t;
     keysI[2 * t] = ((uint64_t)(uint32_t)ti[t] << ebits) | (uint64_t)(2 * t);
     keysI[2 * t + 1] = ((uint64_t)(uint32_t)tj[t] << ebits) | (uint64_t)(2 * t + 1);
@@ -674,8 +679,17 @@ extern "C" int eb_bpr_exact_f64(double *U, double *V, double *item_bias, int d, 
     const int ebits = bits_for((uint64_t)(2 * n));
     const int rbits_u = bits_for((uint64_t)n_users), rbits_i = bits_for((uint64_t)n_items);
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    make_keys_kernel<<<blocks, 256, 0, st>>>(tu, ti, tj, n, ebits, keys_in, keys_in + n);
+    int32_t *status = cnt + (size_t)n_users + (size_t)n_items + 8;
+    EB_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    make_keys_kernel<<<blocks, 256, 0, st>>>(tu, ti, tj, n, ebits, keys_in, keys_in + n, n_users, n_items, status);
     EB_CUDA(cudaGetLastError());
+    {   // exact mode is latency-insensitive (one call per epoch): validate synchronously rather than risk a spin that never ends
+        int32_t bad = 0;
+        EB_CUDA(cudaMemcpyAsync(&bad, status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EB_CUDA(cudaStreamSynchronize(st));
+        if (bad & 2) return set_err(EB_ERR_ARG, "triple ids out of range (need u < %d, i and j < %d)", n_users, n_items);
+        if (bad & 1) return set_err(EB_ERR_ARG, "a triple has i == j (the reference sampler never emits one, custom_sampler.py:39-41)");
+    }
     size_t cb = L.cub_bytes;
     EB_CUDA(cub::DeviceRadixSort::SortKeys(ws + L.cub, cb, keys_in, keys_out, n, 0, ebits + rbits_u, st));
     ranks_kernel<<<blocks, 256, 0, st>>>(keys_out, n, ebits, 0, ku, nullptr);

@@ -136,7 +136,6 @@ class BPRMF(RecMixin, BaseRecommenderModel):
         if self._mode == "hogwild" and not hasattr(self._params, "b200_eval"):
             self._params.b200_eval = "device"          # throughput mode: metrics straight from the top-k tensor
         self._batch_size = 1                                    # BPRMF.py:80 (YAML batch_size ignored)
-        self._ratings = self._data.train_dict
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.BPRMF needs a CUDA device (there is no CPU fallback)")

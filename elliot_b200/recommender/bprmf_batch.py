@@ -100,7 +100,6 @@ class BPRMF_batch(RecMixin, BaseRecommenderModel):
         self.autoset_params()
         if self._batch_size < 1:
             self._batch_size = self._data.transactions                 # BPRMF_batch.py:74-75
-        self._ratings = self._data.train_dict
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.BPRMF_batch needs a CUDA device (there is no CPU fallback)")
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))

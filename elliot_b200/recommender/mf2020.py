@@ -130,7 +130,6 @@ class MF2020(RecMixin, BaseRecommenderModel):
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.MF2020 needs a CUDA device (there is no CPU fallback)")
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
-        self._ratings = self._data.train_dict
         self._batch_size = 100000                                     # MF.py:68-69 (progress-bar granularity only)
         # MF.py:65-76: the sampler is built first, the model second; both seed the global streams with the model
         # seed and only the model draws before training, so one numpy stream (init, then negatives) serves both

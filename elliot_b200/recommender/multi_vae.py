@@ -213,7 +213,6 @@ class MultiVAE(RecMixin, BaseRecommenderModel):
             ("_dropout_rate", "dropout_pkeep", "dropout_pkeep", 1, None, None),
         ]
         self.autoset_params()
-        self._ratings = self._data.train_dict
         random.seed(42)                                              # sparse_sampler.py:10
         if self._batch_size < 1:
             self._batch_size = self._num_users

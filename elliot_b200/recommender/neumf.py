@@ -176,7 +176,6 @@ class NeuMF(RecMixin, BaseRecommenderModel):
             raise NotImplementedError("elliot_b200.NeuMF covers the default configuration: dropout 0, both branches trained")
         if not torch.cuda.is_available():
             raise RuntimeError("elliot_b200.NeuMF needs a CUDA device (there is no CPU fallback)")
-        self._ratings = self._data.train_dict
         self._device = torch.device(getattr(self._params, "b200_device", "cuda:0"))
         self._indptr, _, self._sorted_idx = train_csr_of(self._data, self._device, set_order=False)
         self._model = NeuralMatrixFactorizationModel(self._num_users, self._num_items, self._mf_factors, self._learning_rate,

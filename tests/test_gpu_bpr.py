@@ -270,6 +270,20 @@ def test_fused_sampled_step_equals_sample_then_step(golden_small):
     assert (Ud.cpu().numpy()[:, :d] != g["U0"].astype(np.float32)).any()
 
 
+def test_exact_mode_rejects_triples_it_cannot_order():
+    """i == j would make the ordered kernel wait on one row counter twice: it must be refused, not spin."""
+    from elliot_b200._lib import EbError
+    U = torch.zeros((4, 8), dtype=torch.float64, device=DEV); V = torch.zeros((5, 8), dtype=torch.float64, device=DEV)
+    b = torch.zeros(5, dtype=torch.float64, device=DEV)
+    t = lambda *a: torch.tensor(a, dtype=torch.int32, device=DEV)
+    with pytest.raises(EbError, match="i == j"):
+        ops.bpr_exact_f64(U, V, b, 8, t(0, 1), t(2, 3), t(4, 3), 0.05, 0, 0, 0, 0)
+    with pytest.raises(EbError, match="out of range"):
+        ops.bpr_exact_f64(U, V, b, 8, t(0, 9), t(2, 3), t(4, 1), 0.05, 0, 0, 0, 0)
+    ops.bpr_exact_f64(U, V, b, 8, t(0, 1), t(2, 3), t(4, 1), 0.05, 0, 0, 0, 0)        # a valid batch still runs
+    torch.cuda.synchronize()
+
+
 def test_bad_arguments_raise():
     from elliot_b200._lib import EbError
     U = torch.zeros((4, 12), dtype=torch.float32, device=DEV)   # stride 12 is not a supported row stride
