@@ -88,6 +88,12 @@ SIGNATURES = {
                          c_void, c_size, c_void]),
     "eb_partition_streams_create": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(c_int)]),
     "eb_table_apply_delta_late_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_void]),
+    "eb_gmf_step_grads": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void,
+                                  c_void, c_void]),
+    "eb_gmf_scale_rows": (c_int, [c_void, c_i64, c_i64, c_int, c_void, c_void, c_i64, c_void]),
+    "eb_sigmoid_inplace": (c_int, [c_void, c_i64, c_void]),
+    "eb_pointwise_sample_philox": (c_int, [c_i32, c_i32, c_void, c_void, c_void, c_int, c_i64, c_u64, c_u64, c_void, c_void, c_void,
+                                           c_void]),
     "eb_peer_alloc": (c_int, [c_size, ctypes.POINTER(ctypes.c_void_p)]),
     "eb_peer_free": (c_int, [c_void]),
     "eb_peer_export": (c_int, [c_void, c_void]),

@@ -281,6 +281,21 @@ __global__ void __launch_bounds__(256) philox_sample_kernel(const HogwildParams 
     }
 }
 
+// pointwise_pos_neg_sampler.py:24-48: u uniform; one fair bit decides between a uniform train item of u (label 1) and a
+// uniform non-train item (label 0).  The BPR sampler already draws both for u: keep one of them.
+__global__ void __launch_bounds__(256) pointwise_sample_kernel(const HogwildParams p, float *__restrict__ out_label) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < p.n; t += stride) {
+        int u, i, j;
+        sample_triple(p, t, u, i, j);
+        uint32_t r[4];
+        Philox::gen(p.seed, p.first + (uint64_t)t, 0x20000000u, r);
+        const bool pos = (r[0] >> 31) != 0;
+        p.out_u[t] = u; p.out_i[t] = pos ? i : j; out_label[t] = pos ? 1.f : 0.f;
+    }
+}
+
 template <int DP, bool SAMPLE, bool ATOMIC, bool PEER = false>
 static int launch_hogwild_t(const HogwildParams &p, int reserve_sms, cudaStream_t st) {
     int per_sm = 0;
@@ -631,6 +646,24 @@ extern "C" int eb_bpr_sample_philox_filter(int32_t n_users, int32_t n_items, con
     int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
     philox_sample_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+extern "C" int eb_pointwise_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr, const int32_t *csr_indices,
+                                          const uint32_t *filter, int filter_words, int64_t n, uint64_t seed, uint64_t first,
+                                          int32_t *out_u, int32_t *out_i, float *out_label, void *stream) {
+    EB_ARG(n >= 0 && n_users > 0 && n_items > 1, "bad sizes");
+    EB_ARG(csr_indptr && csr_indices && out_u && out_i && out_label, "null pointer");
+    if (n == 0) return EB_OK;
+    HogwildParams p{};
+    p.n = n; p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
+    p.seed = seed; p.first = first; p.out_u = out_u; p.out_i = out_i;
+    if (int rc = set_filter(p, filter, filter_words)) return rc;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    pointwise_sample_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p, out_label);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

@@ -630,3 +630,36 @@ def gather_rows_peer_f32(shards, shard_rows, ld, ids, width, out=None):
         out = torch.empty((ids.numel(), width), dtype=torch.float32, device=ids.device)
     _call("eb_gather_rows_peer_f32", ids, sa, n, shard_rows, ld, _ptr(ids), ids.numel(), width, _ptr(out), out.stride(0))
     return out
+
+
+# ---------------------------------------------------------------- GMF (csrc/gmf.cu)
+def pointwise_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0, filter=None):
+    """(u, item, label) samples of pointwise_pos_neg_sampler.py:24-48 (Philox stream)."""
+    _need_cuda(indptr, indices, filter)
+    dev = indptr.device
+    u = torch.empty(n, dtype=torch.int32, device=dev); i = torch.empty_like(u); y = torch.empty(n, dtype=torch.float32, device=dev)
+    _call("eb_pointwise_sample_philox", indptr, n_users, n_items, _ptr(indptr), _ptr(indices), _ptr(filter),
+          0 if filter is None else filter.shape[1], n, seed, first, _ptr(u), _ptr(i), _ptr(y))
+    return u, i, y
+
+
+def gmf_step_grads(U, I, h, f, u, it, label, dU, dI, dh, loss=None, mean_over=None):
+    _need_cuda(U, I, h, u, it, label, dU, dI, dh, loss); _chk_idx(u, it)
+    assert U.stride(0) == I.stride(0) == dU.stride(0) == dI.stride(0)
+    _call("eb_gmf_step_grads", U, _ptr(U), _ptr(I), U.stride(0), f, _ptr(h), _ptr(u), _ptr(it), _ptr(label), u.numel(),
+          int(mean_over) if mean_over else max(int(u.numel()), 1), _ptr(dU), _ptr(dI), _ptr(dh), _ptr(loss))
+
+
+def gmf_scale_rows(src, h, f, out=None):
+    _need_cuda(src, h, out)
+    if out is None:
+        out = torch.zeros_like(src)
+    _call("eb_gmf_scale_rows", src, _ptr(src), src.stride(0), src.shape[0], f, _ptr(h), _ptr(out), out.stride(0))
+    return out
+
+
+def sigmoid_(x):
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    _call("eb_sigmoid_inplace", x, _ptr(x), x.numel())
+    return x

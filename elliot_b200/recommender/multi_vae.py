@@ -42,9 +42,10 @@ class VariationalAutoEncoder:
             torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=g)
             return t
         I, H, L = self.I, self.H, self.L
+        Z = self._code_width()                         # 2L: mean | log-variance (one draw per Dense in the reference too)
         # W1 as [I][H] (gather-friendly); the other kernels as [out][in] = K-major GEMM B-operands
         self.P = {"W1": glorot(I, H, I, H), "b1": torch.zeros(_pad4(H), device=self.device),
-                  "W2": glorot(2 * L, H, H, L), "b2": torch.zeros(_pad4(2 * L), device=self.device),
+                  "W2": glorot(Z, H, H, L), "b2": torch.zeros(_pad4(Z), device=self.device),
                   "W3": glorot(H, L, L, H), "b3": torch.zeros(_pad4(H), device=self.device),
                   "W4": glorot(I, H, H, I), "b4": torch.zeros(_pad4(I), device=self.device)}
         z = lambda t: torch.zeros_like(t)
@@ -60,6 +61,9 @@ class VariationalAutoEncoder:
         self.step = 0
         self._acc = torch.zeros(2, dtype=torch.float64, device=self.device)      # [kl_sum, nll_sum]
         self._refresh()
+
+    def _code_width(self):
+        return 2 * self.L
 
     def enable_data_parallel(self, group=None):
         """Replicated weights, batch split across the ranks of `group`, gradients averaged by one all-reduce

@@ -341,6 +341,23 @@ int eb_bpr_step_rows_f32(float *U, int64_t ldu, const int32_t *tu, const float *
                          float *dRj, double *loss, void *stream);
 
 /* ------------------------------------------------------------------------
+ * GMF (neural/GeneralizedMF/generalized_matrix_factorization_model.py:18-92, is_edge_weight_train = True):
+ * out = sigmoid((U[u]*I[i]).h), BinaryCrossentropy (mean over `mean_over` samples).  One fused kernel per batch gathers,
+ * scores, and scatters the gradients into the dense tables dU/dI (+ dh, loss) for the dense Keras Adam that follows.
+ * eb_pointwise_sample_philox: dataset/samplers/pointwise_pos_neg_sampler.py:24-48 (u uniform; a fair bit picks a train item
+ * with label 1 or a non-train item with label 0), Philox stream.  eb_gmf_scale_rows: dst = src * h per column (scoring then
+ * ranks plain dot products); eb_sigmoid_inplace: logits -> probabilities (-inf -> 0).
+ * ------------------------------------------------------------------------ */
+int eb_gmf_step_grads(const float *U, const float *I, int64_t ld, int f, const float *h, const int32_t *u, const int32_t *it,
+                      const float *label, int64_t n, int64_t mean_over, float *dU, float *dI, float *dh, double *loss,
+                      void *stream);
+int eb_gmf_scale_rows(const float *src, int64_t ld, int64_t rows, int f, const float *h, float *dst, int64_t ldd, void *stream);
+int eb_sigmoid_inplace(float *x, int64_t n, void *stream);
+int eb_pointwise_sample_philox(int32_t n_users, int32_t n_items, const int64_t *csr_indptr, const int32_t *csr_indices,
+                               const uint32_t *filter, int filter_words, int64_t n, uint64_t seed, uint64_t first,
+                               int32_t *out_u, int32_t *out_i, float *out_label, void *stream);
+
+/* ------------------------------------------------------------------------
  * Tables spread over the GPUs of one NVSwitch box, addressed DIRECTLY by the kernels (SURVEY.md §8e;
  * no reference counterpart: the reference is single-device).  One process per GPU: a rank allocates its
  * part with eb_peer_alloc (the one place this library allocates: the memory must be a plain cudaMalloc

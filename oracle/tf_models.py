@@ -138,3 +138,46 @@ def neumf_forward_backward(P, u, i, y):
     np.add.at(G["U_mf"], u, dpm * P["I_mf"][i]); np.add.at(G["I_mf"], i, dpm * P["U_mf"][u])
     np.add.at(G["U_mlp"], u, dx0[:, :f]); np.add.at(G["I_mlp"], i, dx0[:, f:])
     return loss, G, p
+
+
+# ---------------------------------------------------------------- MultiDAE (parity unpinned)
+def multidae_forward_backward(P, X):
+    """DenoisingAutoEncoder.call/train_step (autoencoders/dae/multi_dae_model.py:20-125), dropout 0: l2-normalised rows ->
+    tanh Dense(I->H) -> tanh Dense(H->L) -> tanh Dense(L->H) -> Dense(H->I); loss = -mean_u sum_i log_softmax * x.
+    P in Keras layout: W1 (I x H), b1, W2 (H x L), b2, W3 (L x H), b3, W4 (H x I), b4.  Returns loss, grads, logits."""
+    B = X.shape[0]
+    nrm = np.sqrt((X ** 2).sum(1, keepdims=True)); nrm[nrm == 0] = 1.0
+    xh = X / nrm
+    h1 = np.tanh(xh @ P["W1"] + P["b1"])
+    zm = np.tanh(h1 @ P["W2"] + P["b2"])
+    h2 = np.tanh(zm @ P["W3"] + P["b3"])
+    logits = h2 @ P["W4"] + P["b4"]
+    m = logits.max(1, keepdims=True)
+    ls = logits - (m + np.log(np.exp(logits - m).sum(1, keepdims=True)))
+    loss = -np.mean((ls * X).sum(1))
+    dlogits = (np.exp(ls) * X.sum(1, keepdims=True) - X) / B
+    G = {"W4": h2.T @ dlogits, "b4": dlogits.sum(0)}
+    dpre2 = (dlogits @ P["W4"].T) * (1 - h2 ** 2)
+    G["W3"] = zm.T @ dpre2; G["b3"] = dpre2.sum(0)
+    dprez = (dpre2 @ P["W3"].T) * (1 - zm ** 2)
+    G["W2"] = h1.T @ dprez; G["b2"] = dprez.sum(0)
+    dpre1 = (dprez @ P["W2"].T) * (1 - h1 ** 2)
+    G["W1"] = xh.T @ dpre1; G["b1"] = dpre1.sum(0)
+    return loss, G, logits
+
+
+# ---------------------------------------------------------------- GMF (parity unpinned)
+def gmf_forward_backward(P, u, i, y):
+    """GeneralizedMatrixFactorizationModel.call/train_step (generalized_matrix_factorization_model.py:56-75),
+    is_edge_weight_train = True: p = sigmoid((U[u]*I[i]) @ h), Keras BinaryCrossentropy (batch mean, p clipped to
+    [1e-7, 1-1e-7]).  P: U, I (tables), h (f).  Returns loss, grads, p."""
+    B = len(u)
+    pm = P["U"][u] * P["I"][i]
+    p = 1 / (1 + np.exp(-(pm @ P["h"])))
+    pc = np.clip(p, 1e-7, 1 - 1e-7)
+    loss = np.mean(-(y * np.log(pc) + (1 - y) * np.log(1 - pc)))
+    dl = np.where((p > 1e-7) & (p < 1 - 1e-7), p - y, 0.0) / B
+    G = {"h": pm.T @ dl, "U": np.zeros_like(P["U"]), "I": np.zeros_like(P["I"])}
+    dpm = dl[:, None] * P["h"][None, :]
+    np.add.at(G["U"], u, dpm * P["I"][i]); np.add.at(G["I"], i, dpm * P["U"][u])
+    return loss, G, p

@@ -77,6 +77,41 @@ def test_neumf_gradients_match_autograd():
         assert np.abs(np.asarray(G[k]) - tp[k].grad.numpy()).max() < 1e-12, k
 
 
+def test_multidae_gradients_match_autograd():
+    rs = np.random.RandomState(3)
+    B, I, H, L = 10, 40, 16, 8
+    P = {"W1": rs.normal(0, 0.2, (I, H)), "b1": rs.normal(0, 0.05, H), "W2": rs.normal(0, 0.2, (H, L)), "b2": rs.normal(0, 0.05, L),
+         "W3": rs.normal(0, 0.2, (L, H)), "b3": rs.normal(0, 0.05, H), "W4": rs.normal(0, 0.2, (H, I)), "b4": rs.normal(0, 0.05, I)}
+    X = (rs.rand(B, I) < 0.2).astype(np.float64); X[0] = 0; X[0, 3] = 1
+    loss, G, _ = tfm.multidae_forward_backward(P, X)
+    tp = {k: T(v) for k, v in P.items()}
+    tx = torch.tensor(X)
+    xh = torch.nn.functional.normalize(tx, p=2, dim=1)
+    h = torch.tanh(xh @ tp["W1"] + tp["b1"]); h = torch.tanh(h @ tp["W2"] + tp["b2"]); h = torch.tanh(h @ tp["W3"] + tp["b3"])
+    tl = -torch.mean((torch.log_softmax(h @ tp["W4"] + tp["b4"], 1) * tx).sum(1))
+    tl.backward()
+    assert abs(tl.item() - loss) < 1e-12 * abs(loss)
+    for k in P:
+        assert np.abs(G[k] - tp[k].grad.numpy()).max() < 1e-12, k
+
+
+def test_gmf_gradients_match_autograd():
+    rs = np.random.RandomState(4)
+    nu, ni, f, B = 20, 25, 6, 80
+    P = {"U": rs.normal(0, 0.4, (nu, f)), "I": rs.normal(0, 0.4, (ni, f)), "h": rs.normal(0, 0.5, f)}
+    u, i = rs.randint(nu, size=B), rs.randint(ni, size=B)
+    y = (rs.rand(B) < 0.5).astype(np.float64)
+    loss, G, _ = tfm.gmf_forward_backward(P, u, i, y)
+    tp = {k: T(v) for k, v in P.items()}
+    p = torch.clamp(torch.sigmoid((tp["U"][u] * tp["I"][i]) @ tp["h"]), 1e-7, 1 - 1e-7)
+    ty = torch.tensor(y)
+    tl = torch.mean(-(ty * torch.log(p) + (1 - ty) * torch.log(1 - p)))
+    tl.backward()
+    assert abs(tl.item() - loss) < 1e-12 * abs(loss)
+    for k in P:
+        assert np.abs(G[k] - tp[k].grad.numpy()).max() < 1e-12, k
+
+
 def test_keras_adam_restatement_first_steps():
     """KerasAdam against the closed form of its own first steps (lr_t, epsilon placement as documented for TF 2.3)."""
     opt = tfm.KerasAdam(0.01)
