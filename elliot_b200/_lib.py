@@ -32,6 +32,8 @@ SIGNATURES = {
                                      c_void]),
     "eb_bpr_step_host_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void, c_i64,
                                      c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void, c_int, c_void]),
+    "eb_bpr_step_host_packed_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void, c_i64, c_int, c_int,
+                                            c_f32, c_f32, c_f32, c_f32, c_f32, c_void, c_void, c_void, c_int, c_void]),
     "eb_bpr_exact_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
     "eb_bpr_exact_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i32, c_i32, c_void, c_void, c_void, c_i64,
                                  c_f64, c_f64, c_f64, c_f64, c_f64, c_void, c_void, c_size, c_void]),

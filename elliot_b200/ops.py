@@ -111,6 +111,34 @@ def bpr_step_host_f32(U, V, b, d, tu_host, ti_host, tj_host, lr, reg_u, reg_b, r
                                          _stream(U)))
 
 
+def pack_bits(n_users, n_items):
+    """(bits_u, bits_i) of the packed host-triple format."""
+    bu, bi = max(1, (int(n_users) - 1).bit_length()), max(1, (int(n_items) - 1).bit_length())
+    if bu + 2 * bi > 64:
+        raise ValueError("ids too wide for the packed 64-bit triple format")
+    return bu, bi
+
+
+def pack_triples(tu, ti, tj, n_users, n_items):
+    """int64 tensor (same device as the inputs): u | i << bits_u | j << (bits_u + bits_i) — the host-boundary format of
+    bpr_step_host_packed_f32 (8 B/triple)."""
+    bu, bi = pack_bits(n_users, n_items)
+    return tu.to(torch.int64) | (ti.to(torch.int64) << bu) | (tj.to(torch.int64) << (bu + bi))
+
+
+def bpr_step_host_packed_f32(U, V, b, d, packed_host, n_users, n_items, lr, reg_u, reg_b, reg_pos, reg_neg, staging, loss_dev,
+                             loss_host, sync=True, reserve_sms=0):
+    """End-to-end step from HOST (pinned) packed triples: one H2D copy of 8 B/triple, kernel, loss D2H."""
+    _need_cuda(U, V, b, staging, loss_dev)
+    n = packed_host.numel()
+    assert not packed_host.is_cuda and packed_host.dtype == torch.int64 and staging.dtype == torch.int64 and staging.numel() >= n
+    bu, bi = pack_bits(n_users, n_items)
+    with torch.cuda.device(U.device):
+        check(lib().eb_bpr_step_host_packed_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), _ptr(packed_host), n, bu, bi,
+                                                lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(staging), _ptr(loss_dev), _ptr(loss_host),
+                                                (0 if sync else 2) | ((int(reserve_sms) & 0xff) << 8), _stream(U)))
+
+
 class _Workspace:
     """Grow-only device scratch buffer (the C ABI never allocates)."""
 

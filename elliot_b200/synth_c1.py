@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: the synthetic MovieLens-1M-SHAPED interaction file used for BASELINE.json configs[0]
+"""Synthetic data generator (no model arithmetic): the MovieLens-1M-SHAPED interaction file used for BASELINE.json configs[0]
 (sample_hello_world.yml:2-10 names data/movielens_1m/dataset.tsv, which is not shipped and cannot be downloaded here).
 
 6 040 users x 3 706 items, ~1.0 M ratings: per-user counts from a clipped log-normal (min 20 like ML-1M's filter), items

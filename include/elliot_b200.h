@@ -113,6 +113,12 @@ int eb_bpr_step_host_f32(float *U, float *V, float *item_bias, int d, int ld,
                          const int32_t *tu_host, const int32_t *ti_host, const int32_t *tj_host, int64_t n,
                          float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
                          int32_t *staging, double *loss_dev, double *loss_host, int flags, void *stream);
+/* The same with PACKED host triples: one uint64 per triple, u | i << bits_u | j << (bits_u + bits_i)
+ * (bits_u + 2*bits_i <= 64; 20 + 17 + 17 bits cover the C2 shape) — 8 instead of 12 bytes per triple over PCIe and ONE
+ * host-to-device copy instead of three; the kernel unpacks.  staging: device, n uint64. */
+int eb_bpr_step_host_packed_f32(float *U, float *V, float *item_bias, int d, int ld, const uint64_t *packed_host, int64_t n,
+                                int bits_u, int bits_i, float lr, float reg_u, float reg_b, float reg_pos, float reg_neg,
+                                uint64_t *staging, double *loss_dev, double *loss_host, int flags, void *stream);
 
 /* Exact mode: fp64, result identical to applying the n triples strictly one
  * after the other in array order (what the reference does with batch_size

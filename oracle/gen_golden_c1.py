@@ -5,7 +5,7 @@ run_experiment, config_files/sample_hello_world.yml:2-10 shape) by running the U
     elliot.run.run_experiment(<yaml>)   with a `BPRMF:` block (factors 64, 10 epochs, the reference's default
                                         hyper-parameters, seed 42), `strategy: dataset`, `random_subsampling 0.2`
 
-on the synthetic 6 040 x 3 706 / ~1.0 M-rating matrix of oracle/synth_c1.py (MovieLens-1M itself is not shipped and
+on the synthetic 6 040 x 3 706 / ~1.0 M-rating matrix of elliot_b200/synth_c1.py (MovieLens-1M itself is not shipped and
 there is no network).  tensorflow/hyperopt are stubbed for import only (oracle/ref_stubs.py); BPRMF is pure NumPy.
 Captured (tests/golden/bprmf_c1.npz): the reference Evaluator's test metrics after EVERY epoch (a pass-through wrapper
 around Evaluator.eval records them — the reference only logs them), the recommendation lists the reference stored
@@ -25,7 +25,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle import ref_stubs, synth_c1  # noqa: E402
+from oracle import ref_stubs  # noqa: E402
+from elliot_b200 import synth_c1  # noqa: E402
 
 OUT = os.path.join(HERE, "..", "tests", "golden", "bprmf_c1.npz")
 METRICS = ["nDCG", "HR", "Precision", "Recall"]

@@ -284,6 +284,32 @@ def test_exact_mode_rejects_triples_it_cannot_order():
     torch.cuda.synchronize()
 
 
+def test_packed_host_triples_equal_the_three_array_path(golden_small):
+    g = golden_small
+    d = int(g["d"]); ld = ops.padded_dim(d)
+    nu, ni = len(g["users"]), len(g["items"])
+    hp = [float(x) for x in g["hp"]]
+    seen_u, seen_i, keep = set(), set(), []
+    for t in range(len(g["tu"])):                                  # conflict-free subset: the result is order independent
+        u, i, j = g["tu"][t], g["ti"][t], g["tj"][t]
+        if u in seen_u or i in seen_i or j in seen_i: continue
+        seen_u.add(u); seen_i.add(i); seen_i.add(j); keep.append(t)
+    keep = np.array(keep)
+    tu, ti, tj = (torch.from_numpy(g[k][keep].astype(np.int32)) for k in ("tu", "ti", "tj"))
+    packed = ops.pack_triples(tu, ti, tj, nu, ni).pin_memory()
+    bu, bi = ops.pack_bits(nu, ni)
+    assert int(packed[5]) == int(tu[5]) | (int(ti[5]) << bu) | (int(tj[5]) << (bu + bi))
+    Ua, Va = _pad(g["U0"], ld, np.float32), _pad(g["V0"], ld, np.float32); ba = torch.zeros(ni, device=DEV)
+    Ub, Vb = Ua.clone(), Va.clone(); bb = torch.zeros(ni, device=DEV)
+    la = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.bpr_step_f32(Ua, Va, ba, d, tu.to(DEV), ti.to(DEV), tj.to(DEV), *hp, loss=la)
+    staging = torch.empty(packed.numel(), dtype=torch.int64, device=DEV)
+    lb = torch.zeros(1, dtype=torch.float64, device=DEV); lh = torch.zeros(1, dtype=torch.float64).pin_memory()
+    ops.bpr_step_host_packed_f32(Ub, Vb, bb, d, packed, nu, ni, *hp, staging, lb, lh)
+    assert torch.equal(Ua, Ub) and torch.equal(Va, Vb) and torch.equal(ba, bb)
+    assert abs(lh.item() - la.item()) < 1e-9 * abs(la.item())
+
+
 def test_bad_arguments_raise():
     from elliot_b200._lib import EbError
     U = torch.zeros((4, 12), dtype=torch.float32, device=DEV)   # stride 12 is not a supported row stride

@@ -1,6 +1,6 @@
 """BASELINE.json configs[0] / north_star "nDCG@10 within 1e-4 of the reference on the same seed", at C1 scale, through
 the YAML path: the golden tests/golden/bprmf_c1.npz was minted by the UNMODIFIED reference's own
-`elliot.run.run_experiment` (oracle/gen_golden_c1.py) on the ML-1M-shaped synthetic file of oracle/synth_c1.py
+`elliot.run.run_experiment` (oracle/gen_golden_c1.py) on the ML-1M-shaped synthetic file of elliot_b200/synth_c1.py
 (6 040 x 3 706, ~1.0 M ratings, `random_subsampling 0.2`, BPRMF d=64, 10 epochs, seed 42).
 
   exact mode      : every epoch's nDCG/HR/Precision/Recall equals the reference's (asserted <= 1e-4 as the north_star
@@ -16,12 +16,12 @@ import os
 import numpy as np
 import pytest
 
-from oracle import synth_c1
+from elliot_b200 import synth_c1
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bprmf_c1.npz")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOGWILD_TOL = 0.01            # |mean_seeds nDCG@10(hogwild) - nDCG@10(reference)|, absolute
+HOGWILD_TOL = 0.005          # |mean_seeds nDCG@10(hogwild) - nDCG@10(reference)|, absolute (measured: 0.0009; single seeds <= 0.0033)
 OUT = {}
 
 

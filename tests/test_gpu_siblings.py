@@ -86,7 +86,7 @@ def test_gmf_fused_step_matches_restatement():
     assert np.abs(m.P["U"][:, :f].double().cpu().numpy() - want["U"]).max() < 2e-6
     assert np.abs(m.P["h"][:f].double().cpu().numpy() - want["h"]).max() < 2e-6
     # scoring: probabilities of the masked top-k equal sigmoid of the restated logits
-    indptr = torch.zeros(nu + 1, dtype=torch.int64, device=DEV); indices = torch.zeros(0, dtype=torch.int32, device=DEV)
+    indptr = torch.zeros(nu + 1, dtype=torch.int64, device=DEV); indices = torch.zeros(1, dtype=torch.int32, device=DEV)
     idx, val = m.get_recs_topk(5, indptr, indices)
     Pn = {"U": m.P["U"][:, :f].double().cpu().numpy(), "I": m.P["I"][:, :f].double().cpu().numpy(), "h": m.P["h"][:f].double().cpu().numpy()}
     full = 1 / (1 + np.exp(-((Pn["U"] * Pn["h"]) @ Pn["I"].T)))
