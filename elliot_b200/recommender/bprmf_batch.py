@@ -59,7 +59,7 @@ class BPRMFBatchModel:
         if tensor_cores and k <= 16:
             idx, val, _ = ops.score_topk_tc(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices, stats=False)
             return idx, val
-        return ops.score_topk(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices, stats=False)
+        return ops.score_topk(self.Gu, self.Gi, bias, self._factors, k, mask_indptr, mask_indices)
 
     def get_model_state(self):
         F = self._factors

@@ -92,7 +92,7 @@ class MF2020Model:
         if self._mode != "exact" and k <= 16:
             idx, val, _ = ops.score_topk_tc(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices, stats=False)
         else:
-            idx, val = ops.score_topk(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices, stats=False)
+            idx, val = ops.score_topk(self.U, self.V, self.ib, self._factors, k, mask_indptr, mask_indices)
         return idx, val + (self.ub + self.gb).to(val.dtype).unsqueeze(1)
 
     def load_weights(self, path):
