@@ -44,6 +44,7 @@ struct HogwildParams {
     // optional PACKED triples (host boundary: 8 B instead of 12 B per triple over PCIe): u | i << bits_u | j << (bits_u + bits_i)
     const uint64_t *packed;
     int bits_u, bits_i;
+    int no_item_updates;      // profiling only (flags bit 2): item rows are read but not updated
 };
 
 // owner shard and row inside it (one multiply-high and one correction instead of an integer division)
@@ -228,8 +229,10 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                         const int e = (v * G + gl) * 4;
                         if (PEER) {
                             red_add_v4(pu + e, du);
-                            red_add_v4_sys(pi + e, di);
-                            red_add_v4_sys(pj + e, dj);
+                            if (!p.no_item_updates) {
+                                red_add_v4_sys(pi + e, di);
+                                red_add_v4_sys(pj + e, dj);
+                            }
                         } else if (ATOMIC) {
                             red_add_v4(pu + e, du);
                             red_add_v4(pi + e, di);
@@ -630,6 +633,7 @@ extern "C" int eb_bpr_step_sampled_peer_f32(float *U, float *const *V_shards, fl
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    p.no_item_updates = (flags >> 2) & 1;
     if (int rc = set_filter(p, filter, filter_words)) return rc;
     return launch_hogwild_peer<true>(p, ld, flags, (cudaStream_t)stream);
 }

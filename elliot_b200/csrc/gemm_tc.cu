@@ -20,7 +20,11 @@ namespace eb {
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 64, G_STAGES = 4, G_THREADS = 192;
 constexpr int G_STAGE_BYTES = (G_BM + G_BN) * G_BK * 2;      // 32 KB
-constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 256;
+// epilogue staging: every epilogue warp owns two [32 rows x 32 fp32] boxes (128-byte rows, 128B swizzle) that TMA
+// stores (or reduce-adds, split-K) into C as full 128-byte lines while the warp converts the next 32 columns
+constexpr int G_EPI_BOX = 32 * 32 * 4;                       // 4 KB
+constexpr int G_EPI_BYTES = 4 * 2 * G_EPI_BOX;               // 32 KB
+constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + G_EPI_BYTES + 256;
 
 // ---- PTX helpers (same encodings as score_topk_tc.cu)
 __device__ __forceinline__ uint32_t g_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,12 +78,15 @@ struct GemmParams {
     int act;             // 0 none, 1 tanh, 2 relu
     float alpha;         // C = alpha * (A B^T) + bias, then activation
     int splits;          // split-K factor: > 1 -> each work item covers a K range and ADDS into a zeroed C (no bias/act)
+    int tma_store;       // 1: epilogue through shared memory + TMA store / reduce (tmC valid); 0: direct row-per-lane stores
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + G_STAGES * G_STAGE_BYTES);
+    uint8_t *epi = sm + G_STAGES * G_STAGE_BYTES;                          // 1024-byte aligned (stages are 32 KB)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi + G_EPI_BYTES);
     const uint32_t bar0 = g_smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(G_STAGES + s); };
@@ -153,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         const int quad = warp & 3;
-        uint32_t it = 0;
+        uint32_t it = 0, chunk = 0;
         for (int work = blockIdx.x; work < n_tiles; work += gridDim.x, it++) {
             const int tile = work / p.splits, split = work % p.splits;
             const int tm = tile / tiles_n, tn = tile % tiles_n;
@@ -178,6 +185,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     : "r"(taddr + (uint32_t)c0)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.tma_store) {
+                    // ---- coalesced path: lane = row of a [32 x 32] fp32 box in shared memory (16-byte chunk j of row r sits at
+                    // chunk j ^ (r & 7): the 128-byte swizzle TMA expects, and conflict-free for these row-per-lane writes),
+                    // then ONE elected lane hands the box to the TMA unit (store, or reduce-add for split-K)
+                    const int col0 = tn * G_BN + c0;
+                    if (!empty && col0 < p.N && tm * G_BM + quad * 32 < p.M) {         // warp-uniform
+                        const uint32_t box = g_smem_u32(epi + (quad * 2 + (chunk & 1)) * G_EPI_BOX);
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box used 2 chunks ago is read
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            float4 o = make_float4(p.alpha * __uint_as_float(r[c]), p.alpha * __uint_as_float(r[c + 1]),
+                                                   p.alpha * __uint_as_float(r[c + 2]), p.alpha * __uint_as_float(r[c + 3]));
+                            if (p.splits == 1) {
+                                if (p.bias) {
+                                    o.x += __ldg(p.bias + min(col0 + c, p.N - 1)); o.y += __ldg(p.bias + min(col0 + c + 1, p.N - 1));
+                                    o.z += __ldg(p.bias + min(col0 + c + 2, p.N - 1)); o.w += __ldg(p.bias + min(col0 + c + 3, p.N - 1));
+                                }
+                                if (p.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+                                else if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            }
+                            const uint32_t dst = box + (uint32_t)lane * 128u + (uint32_t)(((c >> 2) ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int rr = tm * G_BM + quad * 32;
+                            if (p.splits > 1)
+                                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                             ::"l"(&tmC), "r"(box), "r"(col0), "r"(rr) : "memory");
+                            else
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                             ::"l"(&tmC), "r"(box), "r"(col0), "r"(rr) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        chunk++;
+                    }
+                    continue;
+                }
                 if (row < p.M && !empty) {
                     float *crow = p.C + (int64_t)row * p.ldc;
                     const int col0 = tn * G_BN + c0;
@@ -219,6 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) g_mbar_arrive(ACC_EMPTY(acc));
         }
+        if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all boxes written before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -276,6 +324,27 @@ static int g_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t 
     return EB_OK;
 }
 
+// fp32 C [M][N] (row stride ldc) as {32 cols, 32 rows} boxes, 128-byte swizzle (inner extent = 128 B)
+static int g_make_map_c(CUtensorMap *m, float *C, uint64_t M, uint64_t N, uint64_t ldc) {
+    static GEncodeFn enc = nullptr;
+    if (!enc) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        enc = (GEncodeFn)fp;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled (C) failed with CUresult %d", (int)r);
+    return EB_OK;
+}
+
 }  // namespace eb
 
 using namespace eb;
@@ -303,9 +372,14 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
     EB_ARG(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA strides)");
     EB_ARG(((uintptr_t)A_bf16 % 16) == 0 && ((uintptr_t)B_bf16 % 16) == 0, "operands must be 16-byte aligned");
     EB_ARG(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh) or 2 (relu)");
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mc;
     if (int rc = g_make_map(&ma, A_bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM)) return rc;
     if (int rc = g_make_map(&mb, B_bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, G_BN)) return rc;
+    // TMA needs a 16-byte aligned base and row stride; otherwise (and with EB_GEMM_TMA_STORE=0) the direct-store epilogue runs
+    static const bool tma_off = [] { const char *e = getenv("EB_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
+    const bool tma_store = !tma_off && (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
+    if (tma_store) { if (int rc = g_make_map_c(&mc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc)) return rc; }
+    else mc = ma;
     const int n_out_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
     const int k_blocks = (K + G_BK - 1) / G_BK;
     // split-K: few output tiles with a long K (dh2 = dlogits . W4: 20 tiles, K = 26 744) leave most SMs idle and each
@@ -318,7 +392,7 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
         const int per = (k_blocks + splits - 1) / splits;
         splits = (k_blocks + per - 1) / per;                         // no empty trailing splits
     }
-    GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits};
+    GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits, tma_store ? 1 : 0};
     EB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     if (splits > 1) {
         if (ldc == N) EB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream));
@@ -327,7 +401,7 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
     const int n_tiles = n_out_tiles * splits;
     int grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    gemm_tc_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, p);
+    gemm_tc_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, mc, p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

@@ -611,7 +611,7 @@ def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj,
 
 
 def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u,
-                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0, filter=None):
+                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0, filter=None, _no_item_updates=False):
     """Fused sample+update step with the item table row-sharded over the GPUs of the box (loads / atomics over NVLink)."""
     _need_cuda(U, indptr, indices, loss)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and U.dtype == torch.float32 and U.stride(1) == 1
@@ -624,7 +624,8 @@ def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_i
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_sampled_peer_f32(_ptr(U), va, ba, ns, shard_rows, d, U.stride(0), n_users, n_items, _ptr(indptr),
                                                  _ptr(indices), _ptr(filter), 0 if filter is None else filter.shape[1], n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss),
-                                                 _ptr(ou), _ptr(oi), _ptr(oj), (int(reserve_sms) & 0xff) << 8, _stream(U)))
+                                                 _ptr(ou), _ptr(oi), _ptr(oj), ((int(reserve_sms) & 0xff) << 8) | (4 if _no_item_updates else 0),
+                                                 _stream(U)))
 
 
 def table_reconcile_peer_f32(slice_ptrs, prev_slice, scale, max_ctas=0):

@@ -171,6 +171,19 @@ def _bpr():
                                       42 + rank, ctr[0] * B, *HP, loss=loss)
         ctr[0] += 1
     ms = timed(step, 10, warm=3)
+
+    def step_reads_only():                                       # profiling: the same kernel without the item-row atomics
+        ops.bpr_step_sampled_peer_f32(U, items.ptrs, bias.ptr_array(), items.shard_rows, d, nu_loc, ni_tot, indptr, indices, B,
+                                      42 + rank, ctr[0] * B, *HP, loss=loss, _no_item_updates=True)
+        ctr[0] += 1
+    res["sharded_step_reads_only_ms"] = timed(step_reads_only, 10, warm=2)
+    filt = ops.bloom_build(indptr, indices, nu_loc)
+
+    def step_filter():
+        ops.bpr_step_sampled_peer_f32(U, items.ptrs, bias.ptr_array(), items.shard_rows, d, nu_loc, ni_tot, indptr, indices, B,
+                                      42 + rank, ctr[0] * B, *HP, loss=loss, filter=filt)
+        ctr[0] += 1
+    res["sharded_step_with_filter_ms"] = timed(step_filter, 10, warm=2)
     finite = all_ok(bool(torch.isfinite(items.local).all().item() and torch.isfinite(U).all().item()))
     res.update({"sharded_step_ms": ms, "triples_per_s_all_ranks": B * world / (ms * 1e-3), "triples_per_s_per_gpu": B / (ms * 1e-3),
                 "finite": finite, "shape": f"{nu_loc} local users, {ni_tot} items sharded over {world} GPUs, d={d}, {B} triples/step/rank",
@@ -286,8 +299,8 @@ def _neumf():
              "I_mf": rel(sh.P["I"][:ihi - ilo, :F], ref.P["I_mf"][ilo:ihi]), "I_mlp": rel(sh.P["I"][:ihi - ilo, F:], ref.P["I_mlp"][ilo:ihi]),
              **{k: rel(sh.P[k], ref.P[k]) for k in ("W1", "W2", "W3", "wp")}}
     # scoring over the sharded item table vs the single-GPU model (whose weights differ by <= the diffs above)
-    indptr = torch.zeros(NU + 1, dtype=torch.int64, device=dev); indices = torch.zeros(0, dtype=torch.int32, device=dev)
-    i_s, v_s = sh.get_recs_topk(0, 32, 10, indptr[ulo:], indices)
+    indptr = torch.zeros(NU + 1, dtype=torch.int64, device=dev); indices = torch.zeros(1, dtype=torch.int32, device=dev)
+    i_s, v_s = sh.get_recs_topk(0, 32, 10, indptr[ulo:].contiguous(), indices)
     i_r, v_r = ref.get_recs_topk(ulo, ulo + 32, 10, indptr, indices)
     overlap = float(sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i_s, i_r)) / (32 * 10))
     res.update({"rel_diff_vs_single_gpu": diffs, "topk_overlap_vs_single_gpu": overlap, "topk_max_prob_diff": float((v_s - v_r).abs().max()),
