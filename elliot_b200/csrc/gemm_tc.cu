@@ -6,7 +6,7 @@
 // layers of the reference need once weights are kept as [out][in]
 // (multi_vae_model.py:44-53,72-78; neural_matrix_factorization_model.py:57-70).  Backward GEMMs
 // use the same kernel on transposed copies (tc_convert_transpose_kernel).
-// Structure = score_topk_tc.cu without the top-k: persistent CTAs, warp 0 TMA producer
+// Structure = score_topk_tc.cu without the top-k (PTX wrappers shared through tc_ptx.cuh): persistent CTAs, warp 0 TMA producer
 // (4-stage ring of {A 128x64, B 128x64} bf16 tiles, 128B swizzle), warp 1 tcgen05.mma issuer
 // (M=128, N=128, K=16 per instruction, fp32 accumulators double-buffered in TMEM), warps 2-5
 // epilogue (tcgen05.ld -> bias/activation -> global).
@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace eb {
 
@@ -25,50 +26,6 @@ constexpr int G_STAGE_BYTES = (G_BM + G_BN) * G_BK * 2;      // 32 KB
 constexpr int G_EPI_BOX = 32 * 32 * 4;                       // 4 KB
 constexpr int G_EPI_BYTES = 4 * 2 * G_EPI_BOX;               // 32 KB
 constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + G_EPI_BYTES + 256;
-
-// ---- PTX helpers (same encodings as score_topk_tc.cu)
-__device__ __forceinline__ uint32_t g_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void g_tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t g_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)acc)
-        : "memory");
-}
-__device__ __forceinline__ void g_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 struct GemmParams {
     float *C;
@@ -87,7 +44,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *epi = sm + G_STAGES * G_STAGE_BYTES;                          // 1024-byte aligned (stages are 32 KB)
     uint64_t *bars = reinterpret_cast<uint64_t *>(epi + G_EPI_BYTES);
-    const uint32_t bar0 = g_smem_u32(bars);
+    const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(G_STAGES + s); };
     auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * G_STAGES + a); };
@@ -102,13 +59,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 
     if (threadIdx.x == 0) {
-        if (g_smem_u32(sm) & 1023u) __trap();
-        for (int s = 0; s < G_STAGES; s++) { g_mbar_init(FULL(s), 1); g_mbar_init(EMPTY(s), 1); }
-        for (int a = 0; a < 2; a++) { g_mbar_init(ACC_FULL(a), 1); g_mbar_init(ACC_EMPTY(a), 4); }
+        if (smem_u32(sm) & 1023u) __trap();
+        for (int s = 0; s < G_STAGES; s++) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(2 * G_BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * G_BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -124,11 +81,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tm = tile / tiles_n, tn = tile % tiles_n;
                 const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, k_blocks_all);
                 for (int kb = kb0; kb < kb1; kb++) {
-                    g_mbar_wait(EMPTY(s), ph ^ 1);
-                    g_mbar_expect_tx(FULL(s), G_STAGE_BYTES);
-                    const uint32_t a_dst = g_smem_u32(sm + s * G_STAGE_BYTES), b_dst = a_dst + G_BM * G_BK * 2;
-                    g_tma_load_2d(a_dst, &tmA, FULL(s), kb * G_BK, tm * G_BM);
-                    g_tma_load_2d(b_dst, &tmB, FULL(s), kb * G_BK, tn * G_BN);
+                    mbar_wait(EMPTY(s), ph ^ 1);
+                    mbar_expect_tx(FULL(s), G_STAGE_BYTES);
+                    const uint32_t a_dst = smem_u32(sm + s * G_STAGE_BYTES), b_dst = a_dst + G_BM * G_BK * 2;
+                    tma_load_2d(a_dst, &tmA, FULL(s), kb * G_BK, tm * G_BM);
+                    tma_load_2d(b_dst, &tmB, FULL(s), kb * G_BK, tn * G_BN);
                     if (++s == G_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -142,20 +99,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int split = work % p.splits;
                 const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, k_blocks_all);
                 const int acc = it & 1;
-                g_mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G_BN);
                 for (int kb = kb0; kb < kb1; kb++) {
-                    g_mbar_wait(FULL(s), ph);
+                    mbar_wait(FULL(s), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = g_smem_u32(sm + s * G_STAGE_BYTES), b_addr = a_addr + G_BM * G_BK * 2;
+                    const uint32_t a_addr = smem_u32(sm + s * G_STAGE_BYTES), b_addr = a_addr + G_BM * G_BK * 2;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        g_umma(d_tmem, g_desc_sw128(a_addr + k * 32), g_desc_sw128(b_addr + k * 32), idesc, ((kb - kb0) | k) != 0);
-                    g_commit(EMPTY(s));
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, ((kb - kb0) | k) != 0);
+                    umma_commit(EMPTY(s));
                     if (++s == G_STAGES) { s = 0; ph ^= 1; }
                 }
-                g_commit(ACC_FULL(acc));
+                umma_commit(ACC_FULL(acc));
             }
         }
     } else {
@@ -166,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tm = tile / tiles_n, tn = tile % tiles_n;
             const bool empty = split * kb_per >= k_blocks_all;          // trailing split without k-blocks: nothing was issued
             const int acc = it & 1;
-            g_mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
+            mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = tm * G_BM + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * G_BN);
@@ -191,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // then ONE elected lane hands the box to the TMA unit (store, or reduce-add for split-K)
                     const int col0 = tn * G_BN + c0;
                     if (!empty && col0 < p.N && tm * G_BM + quad * 32 < p.M) {         // warp-uniform
-                        const uint32_t box = g_smem_u32(epi + (quad * 2 + (chunk & 1)) * G_EPI_BOX);
+                        const uint32_t box = smem_u32(epi + (quad * 2 + (chunk & 1)) * G_EPI_BOX);
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box used 2 chunks ago is read
                         __syncwarp();
 #pragma unroll
@@ -264,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) g_mbar_arrive(ACC_EMPTY(acc));
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
         }
         if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all boxes written before the CTA retires
     }

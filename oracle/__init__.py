@@ -2,7 +2,7 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package, and only as the checker.
-The product package ``elliot_b200`` never imports it (tests/test_no_oracle_in_product.py
+The product package ``elliot_b200`` never imports it (tests/test_capi_symbols.py::test_product_never_imports_oracle
 enforces that).
 
 Parity pinning: the reference ships no tests or golden vectors, so

@@ -59,3 +59,13 @@ elif what == "reconcile":
         ops.table_reconcile_peer_f32([t.data_ptr() for t in reps], prev, 0.5)
     torch.cuda.synchronize()
 print("done", what)
+if what == "neumf":
+    from elliot_b200.recommender.neumf_sharded import ShardedNeuMFModel
+    B = 1 << 20
+    sh = ShardedNeuMFModel(2_500_000, 1_000_000, 64, 1e-3, 42, dev, full_init=False)
+    u = torch.randint(0, 2_500_000, (B,), device=dev, dtype=torch.int32); it = torch.randint(0, 1_000_000, (B,), device=dev, dtype=torch.int32)
+    y = (torch.arange(B, device=dev) % 5 == 0).float()
+    for _ in range(3):
+        sh.train_step((u, it, y))
+    torch.cuda.synchronize()
+    print("done neumf")
