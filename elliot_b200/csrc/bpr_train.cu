@@ -15,6 +15,7 @@
 //    a triple waits until each of its three rows has seen exactly the touches that
 //    precede it in the sequence (ranks come from a radix sort of (row, position)).
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -45,6 +46,7 @@ struct HogwildParams {
     const uint64_t *packed;
     int bits_u, bits_i;
     int no_item_updates;      // profiling only (flags bit 2): item rows are read but not updated
+    int no_prefetch;          // profiling only (flags bit 5): register-staged kernel without the L2 prefetch of the rows
 };
 
 // owner shard and row inside it (one multiply-high and one correction instead of an integer division)
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                     u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
                 }
             }
-            if (!PEER) {
+            if (!PEER && !p.no_prefetch) {
                 // the rows are consumed up to 8 rounds later (the groups walk the warp's 32 triples): pull them into
                 // L2 now so that those loads pay L2 instead of HBM latency
                 const char *ru = reinterpret_cast<const char *>(p.U + (int64_t)u * ld);
@@ -262,6 +264,199 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
     }
 }
 
+// ---------------------------------------------------------------- staged variant of the Hogwild kernel
+// Same arithmetic, same sampler, same atomics as bpr_hogwild_kernel; the difference is HOW the three embedding rows of
+// a triple reach the SM.  There every lane group loads "its" rows into registers (4 triples in flight per group, 118
+// registers, 16 warps/SM) and the loads of a round cannot start before the previous round's arithmetic has retired.
+// Here every lane, as soon as it has sampled its triple, hands the three rows to the copy engine
+// (cp.async.bulk global -> shared, completion on a per-warp mbarrier): 3 x TT row copies per warp are in flight with NO
+// register cost, the groups then read the rows from shared memory (conflict-free 128-bit loads).  That is the
+// "128-bit row loads staged through shared memory" layout of the north_star, and it is what lets rows that live in a
+// PEER GPU's memory (PEER mode: 2-3x the latency of local HBM) arrive without stalling the arithmetic.
+// TT rows-triples per warp chunk: 12 KB of shared memory per warp whatever the row length (DP = 32/64/128 floats).
+template <int DP, bool SAMPLE, bool PEER>
+__global__ void __launch_bounds__(256) bpr_hogwild_stage_kernel(const HogwildParams p) {
+    constexpr int NV = DP / 4;                 // float4 per row
+    constexpr int G = NV >= 32 ? 32 : NV;      // lanes per triple
+    constexpr int VPL = NV / G;                // float4 per lane
+    constexpr int ROWB = DP * 4;
+    constexpr int TT = 4096 / ROWB;            // triples per chunk (32 / 16 / 8)
+    constexpr int NGRP = 32 / G;               // triples processed side by side
+    static_assert(TT >= NGRP && TT <= 32 && 32 % TT == 0, "chunk shape");
+    extern __shared__ __align__(128) uint8_t stage_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gl = lane % G, grp = lane / G;
+    uint8_t *wbuf = stage_smem + (size_t)wib * (TT * 3 * ROWB);          // [TT][3][ROWB]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_smem + (size_t)(blockDim.x >> 5) * (TT * 3 * ROWB));
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + wib);
+    const uint32_t wbuf_s = (uint32_t)__cvta_generic_to_shared(wbuf);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t ld = p.ld;
+    float loss_acc = 0.f;
+
+    auto item_row = [&](int i, float *&row, float *&bias) {
+        if constexpr (PEER) {
+            int o, l;
+            shard_of(p, i, o, l);
+            row = p.Vp[o] + (int64_t)l * ld; bias = p.bp[o] + l;
+        } else {
+            row = p.V + (int64_t)i * ld; bias = p.b + i;
+        }
+    };
+
+    for (int64_t tile = warp_id; tile * 32 < p.n; tile += nwarps) {
+        const int64_t t = tile * 32 + lane;
+        int u = -1, i = 0, j = 0;
+        float bi = 0.f, bj = 0.f;
+        float *pu = nullptr, *pi = nullptr, *pj = nullptr, *pbi = nullptr, *pbj = nullptr;
+        if (t < p.n) {
+            if (SAMPLE) {
+                sample_triple(p, t, u, i, j);
+                if (p.out_u) { p.out_u[t] = u; p.out_i[t] = i; p.out_j[t] = j; }
+            } else if (p.packed) {
+                const uint64_t w = __ldg(p.packed + t);
+                u = (int)(w & ((1ull << p.bits_u) - 1));
+                i = (int)((w >> p.bits_u) & ((1ull << p.bits_i) - 1));
+                j = (int)(w >> (p.bits_u + p.bits_i));
+            } else {
+                u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
+            }
+            pu = p.U + (int64_t)u * ld;
+            item_row(i, pi, pbi); item_row(j, pj, pbj);
+        }
+        const bool valid = u >= 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 32; c0 += TT) {
+            const bool mine = valid && lane >= c0 && lane < c0 + TT;
+            const uint32_t nmine = (uint32_t)__popc(__ballot_sync(0xffffffffu, mine));
+            if (nmine == 0) continue;                                              // warp-uniform
+            // the previous chunk's shared-memory reads (generic proxy) are done before the copy engine overwrites the buffer
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nmine * 3u * (uint32_t)ROWB) : "memory");
+            __syncwarp();
+            if (mine) {
+                const uint32_t dst = wbuf_s + (uint32_t)(lane - c0) * (3u * ROWB);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(pu), "r"(ROWB), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + ROWB), "l"(pi), "r"(ROWB), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + 2 * ROWB), "l"(pj), "r"(ROWB), "r"(bar) : "memory");
+                bi = *pbi; bj = *pbj;                                              // biases ride in registers
+            }
+            {   // wait for the chunk's 3 * nmine rows
+                uint32_t ok;
+                do {
+                    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                                 : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+                } while (!ok);
+                phase ^= 1;
+            }
+#pragma unroll 1
+            for (int s = 0; s < TT; s += NGRP) {
+                const int q = s + grp;                                             // triple slot inside the chunk
+                const int src = c0 + q;                                            // lane that sampled it
+                const int cu = __shfl_sync(0xffffffffu, u, src), ci = __shfl_sync(0xffffffffu, i, src), cj = __shfl_sync(0xffffffffu, j, src);
+                const float cbi = __shfl_sync(0xffffffffu, bi, src), cbj = __shfl_sync(0xffffffffu, bj, src);
+                const bool on = cu >= 0;
+                const float4 *su = reinterpret_cast<const float4 *>(wbuf + (size_t)q * (3 * ROWB));
+                float4 a[VPL], vi[VPL], vj[VPL];
+                float part = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    a[v] = su[v * G + gl]; vi[v] = su[NV + v * G + gl]; vj[v] = su[2 * NV + v * G + gl];
+                    part += a[v].x * (vi[v].x - vj[v].x) + a[v].y * (vi[v].y - vj[v].y) + a[v].z * (vi[v].z - vj[v].z) +
+                            a[v].w * (vi[v].w - vj[v].w);
+                }
+                if (!on) part = 0.f;
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (on) {
+                    const float x = part + (cbi - cbj);
+                    const float z = __fdividef(1.f, 1.f + __expf(x));  // BPRMF_model.py:98
+                    if (gl == 0) loss_acc += fmaxf(-x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
+                    float *gu = p.U + (int64_t)cu * ld, *gi, *gj, *gbi, *gbj;
+                    item_row(ci, gi, gbi); item_row(cj, gj, gbj);
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        const float4 av = a[v], bi4 = vi[v], bj4 = vj[v];
+                        float4 du, di, dj, un;
+                        du.x = p.lr * ((bi4.x - bj4.x) * z - p.reg_u * av.x);
+                        du.y = p.lr * ((bi4.y - bj4.y) * z - p.reg_u * av.y);
+                        du.z = p.lr * ((bi4.z - bj4.z) * z - p.reg_u * av.z);
+                        du.w = p.lr * ((bi4.w - bj4.w) * z - p.reg_u * av.w);
+                        un.x = av.x + du.x; un.y = av.y + du.y; un.z = av.z + du.z; un.w = av.w + du.w;
+                        // item rows see the UPDATED user row (view aliasing, BPRMF_model.py:92,109-116)
+                        di.x = p.lr * (un.x * z - p.reg_pos * bi4.x);
+                        di.y = p.lr * (un.y * z - p.reg_pos * bi4.y);
+                        di.z = p.lr * (un.z * z - p.reg_pos * bi4.z);
+                        di.w = p.lr * (un.w * z - p.reg_pos * bi4.w);
+                        dj.x = p.lr * (-un.x * z - p.reg_neg * bj4.x);
+                        dj.y = p.lr * (-un.y * z - p.reg_neg * bj4.y);
+                        dj.z = p.lr * (-un.z * z - p.reg_neg * bj4.z);
+                        dj.w = p.lr * (-un.w * z - p.reg_neg * bj4.w);
+                        const int e = (v * G + gl) * 4;
+                        red_add_v4(gu + e, du);
+                        if (PEER) {
+                            if (!p.no_item_updates) { red_add_v4_sys(gi + e, di); red_add_v4_sys(gj + e, dj); }
+                        } else {
+                            red_add_v4(gi + e, di); red_add_v4(gj + e, dj);
+                        }
+                    }
+                    if (gl == 0) {
+                        const float dbi = p.lr * (z - p.reg_b * cbi), dbj = p.lr * (-z - p.reg_b * cbj);
+                        if (PEER) { red_add_f32_sys(gbi, dbi); red_add_f32_sys(gbj, dbj); }
+                        else { red_add_f32(gbi, dbi); red_add_f32(gbj, dbj); }
+                    }
+                }
+            }
+        }
+    }
+    if (p.loss) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+        if (lane == 0 && loss_acc != 0.f) atomicAdd(p.loss, (double)loss_acc);
+    }
+}
+
+template <int DP, bool SAMPLE, bool PEER>
+static int launch_stage_t(const HogwildParams &p, int reserve_sms, cudaStream_t st) {
+    constexpr int SMEM = 8 * 12288 + 64;                   // 8 warps x 12 KB + mbarriers
+    auto kern = bpr_hogwild_stage_kernel<DP, SAMPLE, PEER>;
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, SMEM));
+    if (per_sm < 1) per_sm = 1;
+    int64_t tiles = (p.n + 31) / 32;
+    int64_t want = (tiles + 7) / 8;
+    int sms = sm_count() - reserve_sms;
+    if (sms < 1) sms = 1;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 256, SMEM, st>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+// staged kernel for the strides it is built for; flags bit 4 (value 16) forces the register-staged kernel
+static bool use_stage(int dp, int flags) {
+    static const int env = [] { const char *e = getenv("EB_HOGWILD_STAGE"); return e ? atoi(e) : -1; }();
+    if (flags & 16) return false;
+    if (flags & 1) return false;                            // racy (non-atomic) mode exists only in the register kernel
+    if (env == 0) return false;
+    return dp == 32 || dp == 64 || dp == 128;
+}
+
 // one warp per user: OR the two signature bits of every train item into the user's words
 __global__ void __launch_bounds__(256) bloom_build_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                                                           int32_t n_users, int log2bits, uint32_t *__restrict__ out) {
@@ -330,6 +525,13 @@ template <bool SAMPLE>
 static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
     const bool atomic = !(flags & 1);
     const int reserve = (flags >> 8) & 0xff;
+    if (use_stage(dp, flags)) {
+        switch (dp) {
+            case 32: return launch_stage_t<32, SAMPLE, false>(p, reserve, st);
+            case 64: return launch_stage_t<64, SAMPLE, false>(p, reserve, st);
+            default: return launch_stage_t<128, SAMPLE, false>(p, reserve, st);
+        }
+    }
 #define EB_CASE(DPV)                                                                           \
     case DPV:                                                                                  \
         return atomic ? launch_hogwild_t<DPV, SAMPLE, true>(p, reserve, st)                           \
@@ -345,6 +547,14 @@ static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_
 template <bool SAMPLE>
 static int launch_hogwild_peer(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
     const int reserve = (flags >> 8) & 0xff;
+    if (use_stage(dp, flags)) {
+        switch (dp) {
+            case 32: return launch_stage_t<32, SAMPLE, true>(p, reserve, st);
+            case 64: return launch_stage_t<64, SAMPLE, true>(p, reserve, st);
+            case 128: return launch_stage_t<128, SAMPLE, true>(p, reserve, st);
+            default: break;
+        }
+    }
     switch (dp) {
         case 32: return launch_hogwild_t<32, SAMPLE, true, true>(p, reserve, st);
         case 64: return launch_hogwild_t<64, SAMPLE, true, true>(p, reserve, st);
@@ -597,6 +807,7 @@ extern "C" int eb_bpr_step_sampled_filter_f32(float *U, float *V, float *item_bi
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
+    p.no_prefetch = (flags >> 5) & 1;
     if (int rc = set_filter(p, filter, filter_words)) return rc;
     return launch_hogwild<true>(p, ld, flags, (cudaStream_t)stream);
 }

@@ -169,19 +169,24 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float *__restrict__
     }
 }
 
-// out[c] = sum_r src[r][c]   (each thread owns one column of a 32-column stripe, rows strided over the CTA's y)
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ src, int R, int C, int64_t ld, float *__restrict__ out) {
+// out[c] = sum_r src[r][c].  Each thread owns one column of a 32-column stripe (coalesced 128-byte row segments), the
+// CTA's 8 warps stride over the rows of its SLAB (blockIdx.y); one slab writes the sums, several slabs add them with
+// atomics into a zeroed `out` (tall matrices: the bias gradients of a 1 M-sample NeuMF batch would otherwise run on
+// cols/32 CTAs and take 13 ms each).
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ src, int R, int C, int64_t ld, float *__restrict__ out,
+                                                     int rows_per_slab) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_slab, r1 = min(R, r0 + rows_per_slab);
     float a = 0.f;
     if (c < C)
-        for (int r = w; r < R; r += 8) a += src[(int64_t)r * ld + c];
+        for (int r = r0 + w; r < r1; r += 8) a += src[(int64_t)r * ld + c];
     part[w][threadIdx.x & 31] = a;
     __syncthreads();
     if (w == 0 && c < C) {
         float t = 0.f;
         for (int k = 0; k < 8; k++) t += part[k][threadIdx.x & 31];
-        out[c] = t;
+        if (gridDim.y == 1) out[c] = t; else atomicAdd(out + c, t);
     }
 }
 
@@ -293,7 +298,17 @@ extern "C" int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int
 
 extern "C" int eb_colsum(const float *src, int rows, int cols, int64_t ld, float *out, void *stream) {
     EB_ARG(src && out && rows >= 1 && cols >= 1 && ld >= cols, "bad argument");
-    colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld, out);
+    const int stripes = (cols + 31) / 32;
+    int slabs = 1;
+    if (rows > 8192) {                                         // short matrices keep the single-slab, fixed-order sum
+        slabs = (sm_count() * 4 + stripes - 1) / stripes;
+        const int max_slabs = (rows + 1023) / 1024;            // at least 1024 rows per slab
+        if (slabs > max_slabs) slabs = max_slabs;
+        if (slabs < 1) slabs = 1;
+    }
+    const int rows_per_slab = (rows + slabs - 1) / slabs;
+    if (slabs > 1) EB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, (cudaStream_t)stream));
+    colsum_kernel<<<dim3((unsigned)stripes, (unsigned)slabs), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld, out, rows_per_slab);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

@@ -72,8 +72,9 @@ def bloom_build(indptr, indices, n_users, words=32):
 
 
 def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u, reg_b, reg_pos,
-                         reg_neg, loss=None, out=None, racy=False, reserve_sms=0, filter=None):
-    """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream).  filter: bloom_build() output."""
+                         reg_neg, loss=None, out=None, racy=False, reserve_sms=0, filter=None, _variant=0):
+    """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream).  filter: bloom_build() output.
+    _variant (profiling): 16 = register-staged kernel instead of the shared-memory-staged one, 32 = without L2 prefetch."""
     _need_cuda(U, V, b, indptr, indices, loss, filter)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     ou = oi = oj = None
@@ -84,7 +85,8 @@ def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed,
         check(lib().eb_bpr_step_sampled_filter_f32(_ptr(U), _ptr(V), _ptr(b), d, U.stride(0), n_users, n_items, _ptr(indptr),
                                                    _ptr(indices), _ptr(filter), 0 if filter is None else filter.shape[1], n, seed,
                                                    first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), _ptr(ou), _ptr(oi),
-                                                   _ptr(oj), (1 if racy else 0) | ((int(reserve_sms) & 0xff) << 8), _stream(U)))
+                                                   _ptr(oj), (1 if racy else 0) | ((int(reserve_sms) & 0xff) << 8) | int(_variant),
+                                                   _stream(U)))
 
 
 def bpr_sample_philox(n_users, n_items, indptr, indices, n, seed, first=0, filter=None):
@@ -611,7 +613,8 @@ def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj,
 
 
 def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u,
-                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0, filter=None, _no_item_updates=False):
+                              reg_b, reg_pos, reg_neg, loss=None, out=None, reserve_sms=0, filter=None, _no_item_updates=False,
+                              _variant=0):
     """Fused sample+update step with the item table row-sharded over the GPUs of the box (loads / atomics over NVLink)."""
     _need_cuda(U, indptr, indices, loss)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32 and U.dtype == torch.float32 and U.stride(1) == 1
@@ -624,7 +627,7 @@ def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_i
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_sampled_peer_f32(_ptr(U), va, ba, ns, shard_rows, d, U.stride(0), n_users, n_items, _ptr(indptr),
                                                  _ptr(indices), _ptr(filter), 0 if filter is None else filter.shape[1], n, seed, first, lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss),
-                                                 _ptr(ou), _ptr(oi), _ptr(oj), ((int(reserve_sms) & 0xff) << 8) | (4 if _no_item_updates else 0),
+                                                 _ptr(ou), _ptr(oi), _ptr(oj), ((int(reserve_sms) & 0xff) << 8) | (4 if _no_item_updates else 0) | int(_variant),
                                                  _stream(U)))
 
 
