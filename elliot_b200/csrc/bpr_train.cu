@@ -46,7 +46,6 @@ struct HogwildParams {
     const uint64_t *packed;
     int bits_u, bits_i;
     int no_item_updates;      // profiling only (flags bit 2): item rows are read but not updated
-    int no_prefetch;          // profiling only (flags bit 5): register-staged kernel without the L2 prefetch of the rows
 };
 
 // owner shard and row inside it (one multiply-high and one correction instead of an integer division)
@@ -165,15 +164,6 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
                 } else {
                     u = __ldg(p.tu + t); i = __ldg(p.ti + t); j = __ldg(p.tj + t);
                 }
-            }
-            if (!PEER && !p.no_prefetch) {
-                // the rows are consumed up to 8 rounds later (the groups walk the warp's 32 triples): pull them into
-                // L2 now so that those loads pay L2 instead of HBM latency
-                const char *ru = reinterpret_cast<const char *>(p.U + (int64_t)u * ld);
-                const char *ri = reinterpret_cast<const char *>(p.V + (int64_t)i * ld);
-                const char *rj = reinterpret_cast<const char *>(p.V + (int64_t)j * ld);
-#pragma unroll
-                for (int b = 0; b < DP * 4; b += 128) { prefetch_l2(ru + b); prefetch_l2(ri + b); prefetch_l2(rj + b); }
             }
         }
         // UNR triples of the group in flight at once: all their row loads are issued before the first reduction
@@ -448,13 +438,18 @@ static int launch_stage_t(const HogwildParams &p, int reserve_sms, cudaStream_t 
     return EB_OK;
 }
 
-// staged kernel for the strides it is built for; flags bit 4 (value 16) forces the register-staged kernel
-static bool use_stage(int dp, int flags) {
+// Which kernel: flags bit 4 (16) forces the register-staged kernel, bit 5 (32) the shared-memory-staged one; otherwise the
+// measured default — on ONE local table the two are within 2 % of each other (profiles/r2_hogwild_ab.json: 0.99 vs 1.01 ms at C2,
+// 1.34 vs 1.37 ms at 2 M items) and the register kernel stays; with the item table spread over peer GPUs the staged kernel is the
+// default (`peer_default`): its row copies are in flight without holding registers while the rows cross NVLink.
+static bool use_stage(int dp, int flags, bool peer_default) {
     static const int env = [] { const char *e = getenv("EB_HOGWILD_STAGE"); return e ? atoi(e) : -1; }();
-    if (flags & 16) return false;
+    if (!(dp == 32 || dp == 64 || dp == 128)) return false;
     if (flags & 1) return false;                            // racy (non-atomic) mode exists only in the register kernel
-    if (env == 0) return false;
-    return dp == 32 || dp == 64 || dp == 128;
+    if (flags & 16) return false;
+    if (flags & 32) return true;
+    if (env >= 0) return env != 0;
+    return peer_default;
 }
 
 // one warp per user: OR the two signature bits of every train item into the user's words
@@ -525,7 +520,7 @@ template <bool SAMPLE>
 static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
     const bool atomic = !(flags & 1);
     const int reserve = (flags >> 8) & 0xff;
-    if (use_stage(dp, flags)) {
+    if (use_stage(dp, flags, false)) {
         switch (dp) {
             case 32: return launch_stage_t<32, SAMPLE, false>(p, reserve, st);
             case 64: return launch_stage_t<64, SAMPLE, false>(p, reserve, st);
@@ -547,7 +542,7 @@ static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_
 template <bool SAMPLE>
 static int launch_hogwild_peer(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
     const int reserve = (flags >> 8) & 0xff;
-    if (use_stage(dp, flags)) {
+    if (use_stage(dp, flags, true)) {
         switch (dp) {
             case 32: return launch_stage_t<32, SAMPLE, true>(p, reserve, st);
             case 64: return launch_stage_t<64, SAMPLE, true>(p, reserve, st);
@@ -807,7 +802,6 @@ extern "C" int eb_bpr_step_sampled_filter_f32(float *U, float *V, float *item_bi
     p.lr = lr; p.reg_u = reg_u; p.reg_b = reg_b; p.reg_pos = reg_pos; p.reg_neg = reg_neg; p.loss = loss;
     p.n_users = n_users; p.n_items = n_items; p.indptr = csr_indptr; p.indices = csr_indices;
     p.seed = seed; p.first = first_triple; p.out_u = out_u; p.out_i = out_i; p.out_j = out_j;
-    p.no_prefetch = (flags >> 5) & 1;
     if (int rc = set_filter(p, filter, filter_words)) return rc;
     return launch_hogwild<true>(p, ld, flags, (cudaStream_t)stream);
 }

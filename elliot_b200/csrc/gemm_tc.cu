@@ -38,6 +38,13 @@ struct GemmParams {
     int tma_store;       // 1: epilogue through shared memory + TMA store / reduce (tmC valid); 0: direct row-per-lane stores
 };
 
+// A_MN / B_MN: the operand is given with its M (resp. N) index contiguous — a [K][M] row-major matrix — instead of K-major.
+// TMA then fetches {64 m, 64 k} boxes (two per 128-wide tile) whose 128-byte rows are 64 consecutive M elements, and the
+// shared-memory descriptor says "MN-major": ((8,n),(8,k)) 16-byte units with strides ((1,LBO),(8,SBO)), LBO = the distance
+// between the two 64-wide M blocks (8 KB), SBO = 8 k-rows (1 KB); one K = 16 step advances 16 k-rows = 2 KB.  The weight-gradient
+// GEMMs dW = dY^T . X (K = the batch) and dX = dY . W with W kept [K][N] read their operands this way, so no transposed
+// bf16 copies of activations or weights are ever written.
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -84,8 +91,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(EMPTY(s), ph ^ 1);
                     mbar_expect_tx(FULL(s), G_STAGE_BYTES);
                     const uint32_t a_dst = smem_u32(sm + s * G_STAGE_BYTES), b_dst = a_dst + G_BM * G_BK * 2;
-                    tma_load_2d(a_dst, &tmA, FULL(s), kb * G_BK, tm * G_BM);
-                    tma_load_2d(b_dst, &tmB, FULL(s), kb * G_BK, tn * G_BN);
+                    if (A_MN) {
+                        tma_load_2d(a_dst, &tmA, FULL(s), tm * G_BM, kb * G_BK);
+                        tma_load_2d(a_dst + 64 * G_BK * 2, &tmA, FULL(s), tm * G_BM + 64, kb * G_BK);
+                    } else {
+                        tma_load_2d(a_dst, &tmA, FULL(s), kb * G_BK, tm * G_BM);
+                    }
+                    if (B_MN) {
+                        tma_load_2d(b_dst, &tmB, FULL(s), tn * G_BN, kb * G_BK);
+                        tma_load_2d(b_dst + 64 * G_BK * 2, &tmB, FULL(s), tn * G_BN + 64, kb * G_BK);
+                    } else {
+                        tma_load_2d(b_dst, &tmB, FULL(s), kb * G_BK, tn * G_BN);
+                    }
                     if (++s == G_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -93,7 +110,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: fp32 accum, bf16 A/B, K-major both, N=128, M=128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24) |
+                                       (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);      // a_major / b_major: 1 = MN-major
             int s = 0; uint32_t ph = 0; uint32_t it = 0;
             for (int work = blockIdx.x; work < n_tiles; work += gridDim.x, it++) {
                 const int split = work % p.splits;
@@ -108,7 +126,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a_addr = smem_u32(sm + s * G_STAGE_BYTES), b_addr = a_addr + G_BM * G_BK * 2;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, ((kb - kb0) | k) != 0);
+                        umma_bf16(d_tmem, A_MN ? umma_desc_sw128_mn(a_addr + k * 2048) : umma_desc_sw128(a_addr + k * 32),
+                                  B_MN ? umma_desc_sw128_mn(b_addr + k * 2048) : umma_desc_sw128(b_addr + k * 32), idesc, ((kb - kb0) | k) != 0);
                     umma_commit(EMPTY(s));
                     if (++s == G_STAGES) { s = 0; ph ^= 1; }
                 }
@@ -260,7 +279,8 @@ typedef CUresult (*GEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, vo
                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int g_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t K, uint64_t ld_elems, uint32_t box_rows) {
+// mn = false: operand [rows][K] (K contiguous), boxes {64 k, box_rows}; mn = true: operand [K][rows] (rows contiguous), boxes {64 rows, 64 k}
+static int g_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t K, uint64_t ld_elems, uint32_t box_rows, bool mn = false) {
     static GEncodeFn enc = nullptr;
     if (!enc) {
         void *fp = nullptr;
@@ -270,9 +290,9 @@ static int g_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t 
             return set_err(EB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
         enc = (GEncodeFn)fp;
     }
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {(cuuint64_t)(mn ? rows : K), (cuuint64_t)(mn ? K : rows)};
     cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-    cuuint32_t box[2] = {G_BK, box_rows};
+    cuuint32_t box[2] = {64, mn ? (cuuint32_t)G_BK : box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -322,16 +342,16 @@ extern "C" int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld,
     return EB_OK;
 }
 
-extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
-                               int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
+static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_bf16, int64_t ldb, bool b_mn, float *C, int64_t ldc,
+                     int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
     EB_ARG(A_bf16 && B_bf16 && C, "null pointer");
-    EB_ARG(M >= 1 && N >= 1 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "bad shape M=%d N=%d K=%d", M, N, K);
+    EB_ARG(M >= 1 && N >= 1 && K >= 1 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldc >= N, "bad shape M=%d N=%d K=%d", M, N, K);
     EB_ARG(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA strides)");
     EB_ARG(((uintptr_t)A_bf16 % 16) == 0 && ((uintptr_t)B_bf16 % 16) == 0, "operands must be 16-byte aligned");
     EB_ARG(act >= 0 && act <= 2, "act must be 0 (none), 1 (tanh) or 2 (relu)");
     CUtensorMap ma, mb, mc;
-    if (int rc = g_make_map(&ma, A_bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM)) return rc;
-    if (int rc = g_make_map(&mb, B_bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, G_BN)) return rc;
+    if (int rc = g_make_map(&ma, A_bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, a_mn)) return rc;
+    if (int rc = g_make_map(&mb, B_bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, G_BN, b_mn)) return rc;
     // TMA needs a 16-byte aligned base and row stride; otherwise (and with EB_GEMM_TMA_STORE=0) the direct-store epilogue runs
     static const bool tma_off = [] { const char *e = getenv("EB_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
     const bool tma_store = !tma_off && (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
@@ -350,7 +370,6 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
         splits = (k_blocks + per - 1) / per;                         // no empty trailing splits
     }
     GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits, tma_store ? 1 : 0};
-    EB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     if (splits > 1) {
         if (ldc == N) EB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream));
         else EB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, (cudaStream_t)stream));
@@ -358,7 +377,26 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
     const int n_tiles = n_out_tiles * splits;
     int grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    gemm_tc_kernel<<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, mc, p);
+#define EB_GEMM_LAUNCH(AM, BM)                                                                                        \
+    do {                                                                                                              \
+        EB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));   \
+        gemm_tc_kernel<AM, BM><<<grid, G_THREADS, G_SMEM, (cudaStream_t)stream>>>(ma, mb, mc, p);                     \
+    } while (0)
+    if (a_mn && b_mn) EB_GEMM_LAUNCH(true, true);
+    else if (a_mn) EB_GEMM_LAUNCH(true, false);
+    else if (b_mn) EB_GEMM_LAUNCH(false, true);
+    else EB_GEMM_LAUNCH(false, false);
+#undef EB_GEMM_LAUNCH
     EB_CUDA(cudaGetLastError());
     return EB_OK;
+}
+
+extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
+                               int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
+    return gemm_bf16(A_bf16, lda, false, B_bf16, ldb, false, C, ldc, M, N, K, bias, alpha, act, stream);
+}
+
+extern "C" int eb_gemm_bf16(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
+                            float *C, int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
+    return gemm_bf16(A_bf16, lda, a_rows_are_k != 0, B_bf16, ldb, b_rows_are_k != 0, C, ldc, M, N, K, bias, alpha, act, stream);
 }

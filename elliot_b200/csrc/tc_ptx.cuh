@@ -95,6 +95,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand tile, 128-byte swizzle (what TMA SWIZZLE_128B writes for a {64 mn, k rows} box of a [K][MN] row-major matrix):
+// 16-byte units ((8,n),(8,k)):((1,LBO),(8,SBO)) — 64 MN elements per 128-byte row, 8 k-rows per 1 KB atom (SBO), the next 64 MN
+// elements one 64-row box further (LBO = 64 * 128 B).  cute::UMMA::make_umma_desc<Major::MN>.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
 // K tail (KP % 64 = 16 or 32 columns): the same K-major tile with a 32-byte (layout 6) or 64-byte (layout 4) swizzle,
 // as TMA SWIZZLE_32B / SWIZZLE_64B writes a {16 | 32 bf16, rows} box: rows 32 / 64 B apart, 8-row groups 256 / 512 B apart.
 template <int KT>

@@ -74,7 +74,7 @@ def bloom_build(indptr, indices, n_users, words=32):
 def bpr_step_sampled_f32(U, V, b, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u, reg_b, reg_pos,
                          reg_neg, loss=None, out=None, racy=False, reserve_sms=0, filter=None, _variant=0):
     """Fused sample+update step (custom_sampler.py:24-46 distribution, Philox stream).  filter: bloom_build() output.
-    _variant (profiling): 16 = register-staged kernel instead of the shared-memory-staged one, 32 = without L2 prefetch."""
+    _variant (profiling): 16 forces the register-staged kernel, 32 the shared-memory-staged one (default: see use_stage)."""
     _need_cuda(U, V, b, indptr, indices, loss, filter)
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     ou = oi = oj = None
@@ -314,6 +314,19 @@ def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
     return out
 
 
+def gemm_bf16(A, B, M, N, K, a_rows_are_k=False, b_rows_are_k=False, bias=None, alpha=1.0, act=0, out=None):
+    """C[M][N] fp32 = act(alpha * op(A) @ op(B)^T + bias): an operand flagged rows_are_k is a [K][M] (resp. [K][N]) row-major
+    bf16 matrix read by the tensor cores as it lies (MN-major descriptors) — the backward GEMMs need no transposed copies."""
+    _need_cuda(A, B, bias, out)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().eb_gemm_bf16(_ptr(A), A.stride(0), 1 if a_rows_are_k else 0, _ptr(B), B.stride(0), 1 if b_rows_are_k else 0,
+                                 _ptr(out), out.stride(0), M, N, K, _ptr(bias), alpha, act, _stream(A)))
+    return out
+
+
 # ---------------------------------------------------------------- MultiVAE: whole step in one call (vae_step.cu)
 class _VaeModelStruct(ctypes.Structure):
     _fields_ = ([("n_items", ctypes.c_int), ("H", ctypes.c_int), ("L", ctypes.c_int), ("reserved", ctypes.c_int)]
@@ -331,9 +344,10 @@ def vae_model_struct(n_items, H, L, P, G, M, V, bf16_copies, indptr, indices):
         for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"):
             assert d[k].dtype == torch.float32 and d[k].is_contiguous()
             setattr(st, pre + k, d[k].data_ptr())
-    for name, t in zip(("W2b", "W3b", "W4b", "W2t", "W3t", "W4t"), bf16_copies):
+    for name, t in zip(("W2b", "W3b", "W4b"), bf16_copies):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()
         setattr(st, name, t.data_ptr())
+    st.W2t = st.W3t = st.W4t = None                      # unused since the backward GEMMs read the [out][in] copies directly
     assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
     st.indptr, st.indices = indptr.data_ptr(), indices.data_ptr()
     st._keep = (P, G, M, V, bf16_copies, indptr, indices)

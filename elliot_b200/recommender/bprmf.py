@@ -150,6 +150,10 @@ class BPRMF(RecMixin, BaseRecommenderModel):
         np.random.seed(42)                                      # keep the host's global stream where the reference leaves it
         self._hog_counter = 0
         self._loss_dev = torch.zeros(1, dtype=torch.float64, device=self._device)
+        # per-user membership signatures shorten the sampler's load chain on large catalogues (+4 % at 2 M items) and cost
+        # ~10 % on small, L2-resident ones (profiles/r2_hogwild_ab.json); the samples are identical either way
+        self._filter = ops.bloom_build(self._indptr, self._sorted_idx, self._num_users) \
+            if self._mode == "hogwild" and self._num_items >= 500_000 else None
 
     @property
     def name(self):
@@ -193,7 +197,8 @@ class BPRMF(RecMixin, BaseRecommenderModel):
                     n = min(self._hog_batch, T - done)
                     ops.bpr_step_sampled_f32(self._model.U, self._model.V, self._model.b, self._factors,
                                              self._num_users, self._num_items, self._indptr, self._sorted_idx, n,
-                                             self._seed, self._hog_counter, *self._model.hyper(), loss=self._loss_dev)
+                                             self._seed, self._hog_counter, *self._model.hyper(), loss=self._loss_dev,
+                                             filter=self._filter)
                     self._hog_counter += n
                     done += n
             self.evaluate(it, float(self._loss_dev.item()))

@@ -45,15 +45,15 @@ class DenoisingAutoEncoder(VariationalAutoEncoder):
         h1, zm, _, h2, logits = self._forward(rows, sid)
         ops.vae_softmax(logits, self.indptr, self.indices, rows, nll_sum=self._acc[1:2], write_grad=True)
         dlogits, G = logits, self.G                                                               # in place
-        dl_b, dl_t = ops.to_bf16(dlogits), ops.to_bf16(dlogits, transpose=True)
-        ops.gemm_bf16_tn(dl_t, ops.to_bf16(h2, transpose=True), I, H, B, out=G["W4"]); ops.colsum(dlogits, G["b4"])
-        dpre2 = ops.tanh_bwd(ops.gemm_bf16_tn(dl_b, self.W4t, B, H, I), h2)
-        ops.gemm_bf16_tn(ops.to_bf16(dpre2, transpose=True), ops.to_bf16(zm, transpose=True), H, L, B, out=G["W3"])
-        ops.colsum(dpre2, G["b3"])
-        dprez = ops.tanh_bwd(ops.gemm_bf16_tn(ops.to_bf16(dpre2), self.W3t, B, L, H), zm)
-        ops.gemm_bf16_tn(ops.to_bf16(dprez, transpose=True), ops.to_bf16(h1, transpose=True), L, H, B, out=G["W2"])
-        ops.colsum(dprez, G["b2"])
-        dpre1 = ops.tanh_bwd(ops.gemm_bf16_tn(ops.to_bf16(dprez), self.W2t, B, H, L), h1)
+        dl_b, h1_b, zm_b, h2_b = ops.to_bf16(dlogits), ops.to_bf16(h1), ops.to_bf16(zm), ops.to_bf16(h2)
+        ops.gemm_bf16(dl_b, h2_b, I, H, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W4"]); ops.colsum(dlogits, G["b4"])
+        dpre2 = ops.tanh_bwd(ops.gemm_bf16(dl_b, self.W4b, B, H, I, b_rows_are_k=True), h2)
+        dpre2_b = ops.to_bf16(dpre2)
+        ops.gemm_bf16(dpre2_b, zm_b, H, L, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W3"]); ops.colsum(dpre2, G["b3"])
+        dprez = ops.tanh_bwd(ops.gemm_bf16(dpre2_b, self.W3b, B, L, H, b_rows_are_k=True), zm)
+        dprez_b = ops.to_bf16(dprez)
+        ops.gemm_bf16(dprez_b, h1_b, L, H, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W2"]); ops.colsum(dprez, G["b2"])
+        dpre1 = ops.tanh_bwd(ops.gemm_bf16(dprez_b, self.W2b, B, H, L, b_rows_are_k=True), h1)
         ops.colsum(dpre1, G["b1"])
         ops.vae_embed_bwd(G["W1"], self.indptr, self.indices, rows, dpre1, self.drop, self.seed * 7919 + sid + self._salt)
 

@@ -75,22 +75,20 @@ class VariationalAutoEncoder:
         self._salt = 0x9E3779B1 * (dist.get_rank(group) if dist.is_initialized() else 0)
 
     def _refresh(self):
-        """bf16 operand copies of the weights in both orientations (after every optimizer step); the buffers are
-        allocated once so the native step can keep their addresses."""
+        """bf16 operand copies of the [out][in] weights (after every optimizer step); the buffers are allocated once so the
+        native step can keep their addresses.  The backward GEMMs read the same copies as [K][N] matrices: there are no
+        transposed copies."""
         P = self.P
         if not hasattr(self, "W2b"):
-            self.W2b = self.W3b = self.W4b = self.W2t = self.W3t = self.W4t = None
+            self.W2b = self.W3b = self.W4b = None
         self.W2b, self.W3b, self.W4b = (ops.to_bf16(P["W2"], out=self.W2b), ops.to_bf16(P["W3"], out=self.W3b),
                                         ops.to_bf16(P["W4"], out=self.W4b))
-        self.W2t, self.W3t, self.W4t = (ops.to_bf16(P["W2"], transpose=True, out=self.W2t),
-                                        ops.to_bf16(P["W3"], transpose=True, out=self.W3t),
-                                        ops.to_bf16(P["W4"], transpose=True, out=self.W4t))
 
     def _native_model(self):
         """The eb_vae_model struct (include/elliot_b200.h) over this model's tensors."""
         if getattr(self, "_cmodel", None) is None:
             self._cmodel = ops.vae_model_struct(self.I, self.H, self.L, self.P, self.G, self.M, self.V,
-                                                (self.W2b, self.W3b, self.W4b, self.W2t, self.W3t, self.W4t),
+                                                (self.W2b, self.W3b, self.W4b),
                                                 self.indptr, self.indices)
         return self._cmodel
 
@@ -142,20 +140,23 @@ class VariationalAutoEncoder:
         h1, ml, z, h2, logits = self._forward(rows, sid, self._acc[0:1])
         ops.vae_softmax(logits, self.indptr, self.indices, rows, nll_sum=self._acc[1:2], write_grad=True)
         dlogits = logits                                                       # in place
-        dl_b, dl_t = ops.to_bf16(dlogits), ops.to_bf16(dlogits, transpose=True)
-        G = self.G
-        ops.gemm_bf16_tn(dl_t, ops.to_bf16(h2, transpose=True), I, H, B, out=G["W4"])
+        # backward GEMMs read the row-major bf16 copies as they lie ("rows are K" operands): no transposed copies
+        dl_b, G = ops.to_bf16(dlogits), self.G
+        h1_b, z_b, h2_b = ops.to_bf16(h1), ops.to_bf16(z), ops.to_bf16(h2)
+        ops.gemm_bf16(dl_b, h2_b, I, H, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W4"])
         ops.colsum(dlogits, G["b4"])
-        dh2 = ops.gemm_bf16_tn(dl_b, self.W4t, B, H, I)
+        dh2 = ops.gemm_bf16(dl_b, self.W4b, B, H, I, b_rows_are_k=True)
         dpre2 = ops.tanh_bwd(dh2, h2)
-        ops.gemm_bf16_tn(ops.to_bf16(dpre2, transpose=True), ops.to_bf16(z, transpose=True), H, L, B, out=G["W3"])
+        dpre2_b = ops.to_bf16(dpre2)
+        ops.gemm_bf16(dpre2_b, z_b, H, L, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W3"])
         ops.colsum(dpre2, G["b3"])
-        dz = ops.gemm_bf16_tn(ops.to_bf16(dpre2), self.W3t, B, L, H)
+        dz = ops.gemm_bf16(dpre2_b, self.W3b, B, L, H, b_rows_are_k=True)
         dml = torch.empty((B, 2 * L), device=self.device)
         ops.vae_reparam_bwd(ml, L, dz, dml, self.seed + self._salt, sid, float(anneal))
-        ops.gemm_bf16_tn(ops.to_bf16(dml, transpose=True), ops.to_bf16(h1, transpose=True), 2 * L, H, B, out=G["W2"])
+        dml_b = ops.to_bf16(dml)
+        ops.gemm_bf16(dml_b, h1_b, 2 * L, H, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W2"])
         ops.colsum(dml, G["b2"])
-        dh1 = ops.gemm_bf16_tn(ops.to_bf16(dml), self.W2t, B, H, 2 * L)
+        dh1 = ops.gemm_bf16(dml_b, self.W2b, B, H, 2 * L, b_rows_are_k=True)
         dpre1 = ops.tanh_bwd(dh1, h1)
         ops.colsum(dpre1, G["b1"])
         ops.vae_embed_bwd(G["W1"], self.indptr, self.indices, rows, dpre1, self.drop, self.seed * 7919 + sid + self._salt)

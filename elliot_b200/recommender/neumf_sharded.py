@@ -94,13 +94,14 @@ class ShardedNeuMFModel:
     def _refresh(self):
         P = self.P
         self.Wb = {k: ops.to_bf16(P[k]) for k in ("W1", "W2", "W3")}
-        self.Wt = {k: ops.to_bf16(P[k], transpose=True) for k in ("W1", "W2", "W3")}
 
     def _mlp(self, x0):
         f, B = self.f, x0.shape[0]
-        h1 = ops.gemm_bf16_tn(ops.to_bf16(x0), self.Wb["W1"], B, 4 * f, 2 * f, bias=self.P["b1"], act=2)
-        h2 = ops.gemm_bf16_tn(ops.to_bf16(h1), self.Wb["W2"], B, 2 * f, 4 * f, bias=self.P["b2"], act=2)
-        h3 = ops.gemm_bf16_tn(ops.to_bf16(h2), self.Wb["W3"], B, f, 2 * f, bias=self.P["b3"], act=2)
+        x0b = ops.to_bf16(x0)
+        h1 = ops.gemm_bf16_tn(x0b, self.Wb["W1"], B, 4 * f, 2 * f, bias=self.P["b1"], act=2); h1b = ops.to_bf16(h1)
+        h2 = ops.gemm_bf16_tn(h1b, self.Wb["W2"], B, 2 * f, 4 * f, bias=self.P["b2"], act=2); h2b = ops.to_bf16(h2)
+        h3 = ops.gemm_bf16_tn(h2b, self.Wb["W3"], B, f, 2 * f, bias=self.P["b3"], act=2)
+        self._act_b = (x0b, h1b, h2b)                     # row-major bf16 copies, read again ("rows are K") by the weight-gradient GEMMs
         return h1, h2, h3
 
     def train_step(self, batch, global_batch=None):
@@ -117,13 +118,18 @@ class ShardedNeuMFModel:
         gb = (global_batch if global_batch is not None else B * self.world) if self.global_mean else B
         ops.neumf_head(pm, h3, f, P["wp"], P["bp"], label=y, dpm=dpm, dh3=dpre3, dwp=G["wp"], dbp=G["bp"], loss=self._loss,
                        mean_over=gb)
-        T = lambda t: ops.to_bf16(t, transpose=True)
-        ops.gemm_bf16_tn(T(dpre3), T(h2), f, 2 * f, B, out=G["W3"]); ops.colsum(dpre3, G["b3"])
-        dpre2 = ops.relu_bwd(ops.gemm_bf16_tn(ops.to_bf16(dpre3), self.Wt["W3"], B, 2 * f, f), h2)
-        ops.gemm_bf16_tn(T(dpre2), T(h1), 2 * f, 4 * f, B, out=G["W2"]); ops.colsum(dpre2, G["b2"])
-        dpre1 = ops.relu_bwd(ops.gemm_bf16_tn(ops.to_bf16(dpre2), self.Wt["W2"], B, 4 * f, 2 * f), h1)
-        ops.gemm_bf16_tn(T(dpre1), T(x0), 4 * f, 2 * f, B, out=G["W1"]); ops.colsum(dpre1, G["b1"])
-        dx0 = ops.gemm_bf16_tn(ops.to_bf16(dpre1), self.Wt["W1"], B, 2 * f, 4 * f)
+        # backward: dW = dY^T . X contracts over the batch rows of both row-major operands, dX = dY . W reads the [out][in] kernel as
+        # a [K][N] matrix — "rows are K" operands of eb_gemm_bf16, no transposed copies of activations or weights
+        x0b, h1b, h2b = self._act_b
+        d3b = ops.to_bf16(dpre3)
+        ops.gemm_bf16(d3b, h2b, f, 2 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W3"]); ops.colsum(dpre3, G["b3"])
+        dpre2 = ops.relu_bwd(ops.gemm_bf16(d3b, self.Wb["W3"], B, 2 * f, f, b_rows_are_k=True), h2)
+        d2b = ops.to_bf16(dpre2)
+        ops.gemm_bf16(d2b, h1b, 2 * f, 4 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W2"]); ops.colsum(dpre2, G["b2"])
+        dpre1 = ops.relu_bwd(ops.gemm_bf16(d2b, self.Wb["W2"], B, 4 * f, 2 * f, b_rows_are_k=True), h1)
+        d1b = ops.to_bf16(dpre1)
+        ops.gemm_bf16(d1b, x0b, 4 * f, 2 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W1"]); ops.colsum(dpre1, G["b1"])
+        dx0 = ops.gemm_bf16(d1b, self.Wb["W1"], B, 2 * f, 4 * f, b_rows_are_k=True)
         ops.neumf_scatter_peer(P["U_mf"], I.ptrs, GI.ptrs, I.shard_rows, 2 * f, f, u, it, dpm, dx0, G["U_mf"], G["U_mlp"])
         if self.world > 1:
             self._loss_f32.copy_(self._loss.to(torch.float32))

@@ -205,10 +205,11 @@ int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr
 int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
 int eb_colsum(const float *src, int rows, int cols, int64_t ld, float *out, void *stream);
 /* One whole MultiVAE training step as ONE native call: the same kernels as the entry points above, issued back to back
- * from C++ (the step is ~47 launches and interpreter-bound when driven from Python).  Replaces
+ * from C++ (the step is ~35 launches).  Replaces
  * VariationalAutoEncoder.train_step (multi_vae_model.py:125-142).  Layouts: W1 [I][H] fp32; W2 [2L][H], W3 [H][L],
  * W4 [I][H] fp32 ([out][in]); biases padded to multiples of 4; g* gradients, m* / v* Adam moments, same shapes;
- * W?b / W?t: bf16 operand copies ([out][pad8(in)] and transposed [in][pad8(out)]), refreshed by phase bit 1.
+ * W?b: bf16 operand copies [out][pad8(in)], refreshed by phase bit 1 (the backward GEMMs read the same copies as
+ * [K][N] matrices through eb_gemm_bf16, so the W?t fields are no longer read and may be NULL).
  * phase: bit 0 = forward + backward (gradients into g*, acc[0] += KL sum term, acc[1] += NLL sum);
  *        bit 1 = Adam (lr_t = lr sqrt(1-b2^step)/(1-b1^step), clears g*) + operand refresh.
  * A data-parallel caller runs phase 1, all-reduces the gradients, then phase 2. */
@@ -332,6 +333,11 @@ int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld, void *dst_
                     void *stream);
 int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t ldb, float *C, int64_t ldc,
                     int M, int N, int K, const float *bias, float alpha, int act, void *stream);
+/* The same contraction with either operand given "rows are K": a_rows_are_k != 0 means A is a [K][M] row-major matrix
+ * (M contiguous, lda >= M), likewise B as [K][N].  The tensor cores read such tiles directly (MN-major shared-memory
+ * descriptors), so the backward GEMMs dW = dY^T . X (K = batch) and dX = dY . W with W kept [K][N] need no transposed copies. */
+int eb_gemm_bf16(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
+                 float *C, int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream);
 
 /* Row-SHARDED tables: owners gather requested rows / add returned deltas; the requester
  * runs the BPR update (BPRMF_model.py:91-117 arithmetic) against fetched item-row copies: user rows are

@@ -37,3 +37,22 @@ def test_convert_transpose_roundtrip():
     C = ops.gemm_bf16_tn(t, t, 77, 77, 301)
     ref = X.bfloat16().double().T @ X.bfloat16().double()
     assert (C.double() - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(600, 200, 512), (26744, 600, 512), (512, 600, 26744), (130, 70, 200), (64, 128, 1 << 20), (1, 8, 8),
+                                  (257, 129, 1000)])
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (True, False), (False, True)])
+def test_gemm_with_rows_are_k_operands(M, N, K, a_mn, b_mn):
+    """An operand stored [K][M] (rows are K) is read through MN-major descriptors: same result as the K-major GEMM on the
+    transposed copy — which is what the backward passes used to build."""
+    if M * N * K > 2e10:
+        pytest.skip("too large")
+    g = torch.Generator(device=DEV); g.manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, device=DEV, generator=g) / K ** 0.5
+    B = torch.randn(N, K, device=DEV, generator=g)
+    Aop = ops.to_bf16(A.T.contiguous()) if a_mn else ops.to_bf16(A)          # [K][M(+pad)] or [M][K(+pad)]
+    Bop = ops.to_bf16(B.T.contiguous()) if b_mn else ops.to_bf16(B)
+    C = ops.gemm_bf16(Aop, Bop, M, N, K, a_rows_are_k=a_mn, b_rows_are_k=b_mn, alpha=0.5)
+    ref = 0.5 * (A.bfloat16().double() @ B.bfloat16().double().T)
+    tol = 2e-4 if K < 100000 else 2e-3                                       # split-K atomics over 1M products
+    assert (C.double() - ref).abs().max().item() < tol

@@ -1,5 +1,5 @@
 """A/B of the fused Hogwild step's variants on one GPU (not the bench contract): shared-memory-staged vs register-staged
-kernel, with / without the per-user membership signatures, with / without the L2 prefetch (register kernel); C2 shape and
+kernel, with / without the per-user membership signatures (an L2 prefetch of the rows was tried and removed: -10 %); C2 shape and
 the large-catalogue shape.  Prints one JSON object; also gpurun_out/hogwild_ab.json."""
 import json
 import os
@@ -43,8 +43,7 @@ for ni in (100_000, 2_000_000):
     filt = ops.bloom_build(ip, ix, nu)
     c = [0]
     res = {}
-    for name, var, f in (("stage+filter", 0, filt), ("stage", 0, None), ("reg+filter+prefetch", 16, filt), ("reg+prefetch", 16, None),
-                         ("reg+filter", 16 | 32, filt), ("reg (round-1 kernel)", 16 | 32, None)):
+    for name, var, f in (("stage+filter", 32, filt), ("stage", 32, None), ("reg+filter", 16, filt), ("reg (round-1 kernel)", 16, None)):
         def st():
             ops.bpr_step_sampled_f32(U, V, b, d, nu, ni, ip, ix, B, 42, c[0] * B, *HP, filter=f, _variant=var)
             c[0] += 1

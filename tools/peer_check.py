@@ -184,6 +184,12 @@ def _bpr():
                                       42 + rank, ctr[0] * B, *HP, loss=loss, filter=filt)
         ctr[0] += 1
     res["sharded_step_with_filter_ms"] = timed(step_filter, 10, warm=2)
+
+    def step_reg():                                              # register-staged kernel instead of the shared-memory-staged default
+        ops.bpr_step_sampled_peer_f32(U, items.ptrs, bias.ptr_array(), items.shard_rows, d, nu_loc, ni_tot, indptr, indices, B,
+                                      42 + rank, ctr[0] * B, *HP, loss=loss, _variant=16)
+        ctr[0] += 1
+    res["sharded_step_register_kernel_ms"] = timed(step_reg, 10, warm=2)
     finite = all_ok(bool(torch.isfinite(items.local).all().item() and torch.isfinite(U).all().item()))
     res.update({"sharded_step_ms": ms, "triples_per_s_all_ranks": B * world / (ms * 1e-3), "triples_per_s_per_gpu": B / (ms * 1e-3),
                 "finite": finite, "shape": f"{nu_loc} local users, {ni_tot} items sharded over {world} GPUs, d={d}, {B} triples/step/rank",
