@@ -305,113 +305,85 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 cnt = (int)res.x; thresh = __uint_as_float(res.y);
             };
 
-            // The accumulator stream of a user block is read as a flat sequence of 64-column chunks, software-pipelined by one
-            // chunk: while chunk g is scanned out of one register set the tcgen05.ld of chunk g+1 is already in flight into the
-            // other, and a tile's TMEM accumulator is handed back to the MMA warp as soon as its last chunk has LANDED in
-            // registers (not after it has been scanned).  One warp per scheduler cannot hide the TMEM round trip any other way.
-            static_assert(NG == 1, "the pipelined epilogue is written for one epilogue warpgroup");
-            constexpr int CPT = BN / 64;                                  // chunks per tile
-            const int total = n_tiles * CPT;
-            auto process = [&](const float (&v)[64], const int col0) {
-                long long t2 = prof ? clock64() : 0;
-                if (DUMP) {
-                    if (valid)
-                        for (int c = 0; c < 64; c++)
-                            if (col0 + c < p.n_items) p.dump[(int64_t)q * p.n_items + col0 + c] = v[c];
-                }
-                // max of each group of 8 columns (fast reject), 3-input max trees
-                float g[8];
-#pragma unroll
-                for (int s8 = 0; s8 < 8; s8++) {
-                    const float *w = v + s8 * 8;
-                    g[s8] = fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(fmaxf(w[3], w[4]), w[5]), fmaxf(w[6], w[7])));
-                }
-                float bm0 = 0.f, bm1 = 0.f;
-                if (HAS_BIAS) { bm0 = __ldg(p.bmax_chunk + (col0 >> 5)); bm1 = __ldg(p.bmax_chunk + min((col0 >> 5) + 1, (p.n_items - 1) >> 5)); }
-                const float m64 = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) + bm0, fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])) + bm1);
-                if (!__any_sync(0xffffffffu, m64 > thresh)) { if (prof) c_scan += clock64() - t2; return; }
-                n_slow++;
-#pragma unroll
-                for (int s8 = 0; s8 < 8; s8++) {
-                    const float bm = s8 < 4 ? bm0 : bm1;
-                    if (!__any_sync(0xffffffffu, g[s8] + bm > thresh)) continue;
-                    n_grp++;
-                    const uint32_t todo = __ballot_sync(0xffffffffu, cnt > TC_BUF - TC_SLACK);
-                    if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > TC_BUF - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
-                    // Append survivors one at a time, largest first: locate the group's max with static
-                    // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
-                    // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
-                    float w8[8];
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        w8[c] = HAS_BIAS ? v[s8 * 8 + c] + __ldg(p.bias + min(col0 + s8 * 8 + c, p.n_items - 1)) : v[s8 * 8 + c];
-                    float gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
+            for (int t = 0; t < n_tiles; t++, tile++) {
+                const int acc = tile & 1;
+                if (NG == 2 && acc != grp) continue;
+                long long t0 = prof ? clock64() : 0;
+                mbar_wait(ACC_FULL(acc), (tile >> 1) & 1);
+                tc_fence_after();
+                if (prof) c_wait += clock64() - t0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-                    for (int round = 0; round < 8; round++) {
-                        if (!__any_sync(0xffffffffu, gm > thresh)) break;
-                        int am = 7;
-#pragma unroll
-                        for (int c = 6; c >= 0; c--) am = (w8[c] == gm) ? c : am;      // first position holding the max
-                        const uint32_t take = gm > thresh ? 1u : 0u;
-                        const int pos = (cnt + row) & 63;
-                        const uint32_t key = tc_key_of(gm, pos);
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.u32 p, %0, 0;\n\t"
-                            "@p st.shared.u32 [%1], %2;\n\t"
-                            "@p st.shared.s32 [%3], %4;\n\t}"
-                            ::"r"(take), "r"(my_key + 4u * (uint32_t)pos), "r"(key), "r"(my_idx + 4u * (uint32_t)pos),
-                              "r"(col0 + s8 * 8 + am)
-                            : "memory");
-                        cnt += (int)take;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) w8[c] = (take && c == am) ? -CUDART_INF_F : w8[c];
-                        gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
+                for (int c0 = 0; c0 < BN; c0 += 64) {
+                    float v[64];
+                    __syncwarp();                     // tcgen05.ld is .sync.aligned
+                    long long t1 = prof ? clock64() : 0;
+                    tmem_ld32_nowait(taddr + (uint32_t)c0, v);
+                    tmem_ld32_nowait(taddr + (uint32_t)c0 + 32u, v + 32);
+                    tmem_ld_wait();
+                    if (prof) c_ld += clock64() - t1;
+                    long long t2 = prof ? clock64() : 0;
+                    const int col0 = t * BN + c0;
+                    if (DUMP) {
+                        if (valid)
+                            for (int c = 0; c < 64; c++)
+                                if (col0 + c < p.n_items) p.dump[(int64_t)q * p.n_items + col0 + c] = v[c];
                     }
-                }
-                if (prof) c_scan += clock64() - t2;
-            };
-            auto issue = [&](int g, float (&v)[64]) {
-                const int tt = g / CPT, c = g - tt * CPT;
-                const uint32_t tl = tile + (uint32_t)tt;
-                const int acc = (int)(tl & 1u);
-                if (c == 0) {
-                    long long t0 = prof ? clock64() : 0;
-                    mbar_wait(ACC_FULL(acc), (tl >> 1) & 1);
-                    tc_fence_after();
-                    if (prof) c_wait += clock64() - t0;
-                }
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN) + (uint32_t)(c * 64);
-                __syncwarp();                                             // tcgen05.ld is .sync.aligned
-                tmem_ld32_nowait(taddr, v);
-                tmem_ld32_nowait(taddr + 32u, v + 32);
-            };
-            auto landed = [&](int g) {
-                long long t1 = prof ? clock64() : 0;
-                tmem_ld_wait();
-                if (prof) c_ld += clock64() - t1;
-                const int tt = g / CPT;
-                if (g - tt * CPT == CPT - 1) {                            // the tile's last chunk is in registers: free the accumulator
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(ACC_EMPTY((int)((tile + (uint32_t)tt) & 1u)));
-                }
-            };
-            {
-                float va[64], vb[64];
-                if (total > 0) issue(0, va);
+                    // max of each group of 8 columns (fast reject), 3-input max trees
+                    float g[8];
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) {
+                        const float *w = v + s8 * 8;
+                        g[s8] = fmaxf(fmaxf(fmaxf(w[0], w[1]), w[2]), fmaxf(fmaxf(fmaxf(w[3], w[4]), w[5]), fmaxf(w[6], w[7])));
+                    }
+                    float bm0 = 0.f, bm1 = 0.f;
+                    if (HAS_BIAS) { bm0 = __ldg(p.bmax_chunk + (col0 >> 5)); bm1 = __ldg(p.bmax_chunk + min((col0 >> 5) + 1, (p.n_items - 1) >> 5)); }
+                    const float m64 = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) + bm0, fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])) + bm1);
+                    if (!__any_sync(0xffffffffu, m64 > thresh)) { if (prof) c_scan += clock64() - t2; continue; }
+                    n_slow++;
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; s8++) {
+                        const float bm = s8 < 4 ? bm0 : bm1;
+                        if (!__any_sync(0xffffffffu, g[s8] + bm > thresh)) continue;
+                        n_grp++;
+                        const uint32_t todo = __ballot_sync(0xffffffffu, cnt > TC_BUF - TC_SLACK);
+                        if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > TC_BUF - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
+                        // Append survivors one at a time, largest first: locate the group's max with static
+                        // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
+                        // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
+                        float w8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++)
+                            w8[c] = HAS_BIAS ? v[s8 * 8 + c] + __ldg(p.bias + min(col0 + s8 * 8 + c, p.n_items - 1)) : v[s8 * 8 + c];
+                        float gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
 #pragma unroll 1
-                for (int g = 0; g < total; g += 2) {
-                    landed(g);
-                    if (g + 1 < total) issue(g + 1, vb);
-                    process(va, (g / CPT) * BN + (g % CPT) * 64);
-                    if (g + 1 < total) {
-                        landed(g + 1);
-                        if (g + 2 < total) issue(g + 2, va);
-                        process(vb, ((g + 1) / CPT) * BN + ((g + 1) % CPT) * 64);
+                        for (int round = 0; round < 8; round++) {
+                            if (!__any_sync(0xffffffffu, gm > thresh)) break;
+                            int am = 7;
+#pragma unroll
+                            for (int c = 6; c >= 0; c--) am = (w8[c] == gm) ? c : am;      // first position holding the max
+                            const uint32_t take = gm > thresh ? 1u : 0u;
+                            const int pos = (cnt + row) & 63;
+                            const uint32_t key = tc_key_of(gm, pos);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.u32 p, %0, 0;\n\t"
+                                "@p st.shared.u32 [%1], %2;\n\t"
+                                "@p st.shared.s32 [%3], %4;\n\t}"
+                                ::"r"(take), "r"(my_key + 4u * (uint32_t)pos), "r"(key), "r"(my_idx + 4u * (uint32_t)pos),
+                                  "r"(col0 + s8 * 8 + am)
+                                : "memory");
+                            cnt += (int)take;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) w8[c] = (take && c == am) ? -CUDART_INF_F : w8[c];
+                            gm = fmaxf(fmaxf(fmaxf(w8[0], w8[1]), w8[2]), fmaxf(fmaxf(fmaxf(w8[3], w8[4]), w8[5]), fmaxf(w8[6], w8[7])));
+                        }
                     }
+                    if (prof) c_scan += clock64() - t2;
                 }
-                tile += (uint32_t)n_tiles;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
             }
             // final compaction: every row ends with its <= KC best unmasked candidates in logical slots 0..cnt-1
             __syncwarp();

@@ -93,7 +93,7 @@ def test_bpr_sampled_peer_draws_the_same_triples_as_the_single_table_kernel(gold
         assert torch.equal(a, c)
     # same triples, same arithmetic; rows hit by several triples see them in a different (Hogwild) order: compare in norm
     rel = lambda a, c: ((a - c).norm() / c.norm().clamp_min(1e-12)).item()
-    assert rel(U1, U2) < 2e-3 and rel(V1, _join(Vs, ni)) < 2e-3 and l2.item() > 0
+    assert rel(U1, U2) < 1e-2 and rel(V1, _join(Vs, ni)) < 1e-2 and l2.item() > 0
     assert (b1 - _join(bs, ni)).abs().max().item() < 0.05
 
 

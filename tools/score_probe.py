@@ -1,5 +1,6 @@
 """Times the tensor-core scoring kernel on C2- and C5-shaped inputs (not the bench contract)."""
-import sys, torch
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elliot_b200 import ops
 dev = "cuda:0"
 def run(nu, ni, d, k, per_user, label):
