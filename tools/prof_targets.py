@@ -27,7 +27,7 @@ if what in ("hogwild", "hogwild_large"):
     nu, ni, d, B = 1_000_000, (100_000 if what == "hogwild" else 2_000_000), 64, 1 << 22
     U = torch.randn(nu, d, device=dev) * 0.1; V = torch.randn(ni, d, device=dev) * 0.1; b = torch.zeros(ni, device=dev)
     ip, ix = csr(nu, ni, 100, 100)
-    f = ops.bloom_build(ip, ix, nu)
+    f = ops.bloom_build(ip, ix, nu) if what == "hogwild_large" else None      # as in bench.py: signatures only on the large catalogue
     for s in range(5):
         ops.bpr_step_sampled_f32(U, V, b, d, nu, ni, ip, ix, B, 42, s * B, *HP, filter=f)
     torch.cuda.synchronize()
