@@ -55,6 +55,8 @@ SIGNATURES = {
                                 c_void]),
     "eb_gemm_bf16": (c_int, [c_void, c_i64, c_int, c_void, c_i64, c_int, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
                              c_void]),
+    "eb_gemm_f32_ref": (c_int, [c_void, c_i64, c_int, c_void, c_i64, c_int, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
+                                c_void]),
     "eb_vae_embed_fwd": (c_int, [c_void, c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_i64, c_f32, c_u64, c_void]),
     "eb_vae_embed_bwd": (c_int, [c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_i64, c_f32, c_u64, c_void]),
     "eb_vae_reparam_fwd": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_i64, c_u64, c_u64, c_void, c_void]),

@@ -288,9 +288,43 @@ def table_apply_delta_f32(cur, prev, delta_sum, scale=1.0):
         check(lib().eb_table_apply_delta_f32(_ptr(cur), _ptr(prev), _ptr(delta_sum), cur.numel(), scale, _stream(cur)))
 
 
+_EXACT_GEMM = False
+
+
+class exact_gemm:
+    """Context manager (tests only): while active, `to_bf16` hands the fp32 tensors through unchanged and the dense layers run
+    on the fp32 CUDA-core checking kernel (eb_gemm_f32_ref) instead of the bf16 tensor-core GEMM.  Models built inside the
+    context can then be compared with their fp64 restatements to ~1e-5 — a check of the model WIRING that bf16 rounding would
+    otherwise blur to 1e-2.  Slow; the product path never enables it; the native one-call MultiVAE step ignores it."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _EXACT_GEMM
+        self.prev, _EXACT_GEMM = _EXACT_GEMM, self.on
+        return self
+
+    def __exit__(self, *a):
+        global _EXACT_GEMM
+        _EXACT_GEMM = self.prev
+
+
+def _gemm_ref(A, B, M, N, K, a_mn, b_mn, bias, alpha, act, out):
+    assert A.dtype == torch.float32 and B.dtype == torch.float32
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().eb_gemm_f32_ref(_ptr(A), A.stride(0), 1 if a_mn else 0, _ptr(B), B.stride(0), 1 if b_mn else 0, _ptr(out),
+                                    out.stride(0), M, N, K, _ptr(bias), alpha, act, _stream(A)))
+    return out
+
+
 def to_bf16(src, transpose=False, out=None):
     """fp32 [R][C] -> bf16 [R][pad8(C)] or (transpose) [C][pad8(R)], zero padded, via eb_convert_bf16."""
     _need_cuda(src)
+    if _EXACT_GEMM:                                       # checking mode: operands stay fp32
+        return src.t().contiguous() if transpose else src
     assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
     R, C = src.shape
     rows, cols = (C, R) if transpose else (R, C)
@@ -305,6 +339,8 @@ def to_bf16(src, transpose=False, out=None):
 def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
     """C[M][N] fp32 = act(alpha * A[M][:K] @ B[N][:K]^T + bias) on the tensor cores (A, B bf16, K-major)."""
     _need_cuda(A, B, bias, out)
+    if A.dtype == torch.float32:                          # exact_gemm checking mode
+        return _gemm_ref(A, B, M, N, K, False, False, bias, alpha, act, out)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
@@ -318,6 +354,8 @@ def gemm_bf16(A, B, M, N, K, a_rows_are_k=False, b_rows_are_k=False, bias=None, 
     """C[M][N] fp32 = act(alpha * op(A) @ op(B)^T + bias): an operand flagged rows_are_k is a [K][M] (resp. [K][N]) row-major
     bf16 matrix read by the tensor cores as it lies (MN-major descriptors) — the backward GEMMs need no transposed copies."""
     _need_cuda(A, B, bias, out)
+    if A.dtype == torch.float32:                          # exact_gemm checking mode
+        return _gemm_ref(A, B, M, N, K, a_rows_are_k, b_rows_are_k, bias, alpha, act, out)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)

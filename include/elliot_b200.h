@@ -338,6 +338,10 @@ int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t
  * descriptors), so the backward GEMMs dW = dY^T . X (K = batch) and dX = dY . W with W kept [K][N] need no transposed copies. */
 int eb_gemm_bf16(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
                  float *C, int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream);
+/* CHECKING path (tests only, slow): the same contraction with fp32 operands on the CUDA cores, fixed-order fp32 FMA
+ * accumulation — lets the dense-layer models be compared with their fp64 restatements to 1e-5 instead of bf16's 1e-2. */
+int eb_gemm_f32_ref(const float *A, int64_t lda, int a_rows_are_k, const float *B, int64_t ldb, int b_rows_are_k, float *C,
+                    int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream);
 
 /* Row-SHARDED tables: owners gather requested rows / add returned deltas; the requester
  * runs the BPR update (BPRMF_model.py:91-117 arithmetic) against fetched item-row copies: user rows are

@@ -116,3 +116,41 @@ def test_native_step_equals_launch_by_launch_sequence(nu, ni, H, L, B, drop):
         rel = ((a.P[k] - b.P[k]).norm() / b.P[k].norm().clamp_min(1e-12)).item()
         assert rel < 5e-4, (k, rel)
     assert torch.equal(a.W4b, ops.to_bf16(a.P["W4"])) and torch.equal(a.W3b, ops.to_bf16(a.P["W3"]))
+
+
+def test_step_wiring_is_exact_with_the_fp32_checking_gemm():
+    """The launch-by-launch sequence with its 8 dense layers on the fp32 checking GEMM (ops.exact_gemm): logits, loss and every
+    gradient agree with the fp64 restatement to 1e-4 — the bf16 tolerance of the tests above hides no wiring error."""
+    nu, ni, H, L, B = 300, 1000, 64, 24, 160
+    rows_np, indptr, indices = _csr(nu, ni, 30, 0)
+    with ops.exact_gemm():
+        m = VariationalAutoEncoder(ni, H, L, 1e-3, 0.0, 0.01, 42, indptr, indices, DEV)
+        m.native = False
+        for k in ("b1", "b2", "b3", "b4"):
+            m.P[k].normal_(0, 0.05)
+        m._refresh()
+        P = {"W1": m.P["W1"].double().cpu().numpy(), "b1": m.P["b1"][:H].double().cpu().numpy(),
+             "W2": m.P["W2"].double().cpu().numpy().T, "b2": m.P["b2"][:2 * L].double().cpu().numpy(),
+             "W3": m.P["W3"].double().cpu().numpy().T, "b3": m.P["b3"][:H].double().cpu().numpy(),
+             "W4": m.P["W4"].double().cpu().numpy().T, "b4": m.P["b4"][:ni].double().cpu().numpy()}
+        batch = np.random.RandomState(1).choice(nu, B, replace=False).astype(np.int32)
+        rows = torch.from_numpy(batch).to(DEV)
+        X = np.zeros((B, ni))
+        for r, u in enumerate(batch):
+            X[r, rows_np[u]] = 1.0
+        anneal, sid = 0.13, 5
+        acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+        h1, ml, z, h2, logits = m._forward(rows, sid, acc[0:1])
+        mu, lv = ml[:, :L].double().cpu().numpy(), ml[:, L:].double().cpu().numpy()
+        eps = (z.double().cpu().numpy() - mu) / np.exp(0.5 * lv)
+        loss_ref, G, (logits_ref, mu_ref, *_rest) = tfm.multivae_forward_backward(P, X, eps, anneal)
+        rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)
+        assert rel(mu, mu_ref) < 1e-5 and rel(logits.double().cpu().numpy(), logits_ref) < 1e-5
+        m.step = sid - 1
+        loss = m.train_step(rows, anneal)
+    assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
+    for k, tr in (("W4", True), ("W3", True), ("W2", True), ("W1", False)):
+        g_ref = G[k].T if tr else G[k]
+        assert rel(m.M[k].double().cpu().numpy() / 0.1, g_ref) < 1e-4, k
+    for k, n in (("b4", ni), ("b3", H), ("b2", 2 * L), ("b1", H)):
+        assert rel(m.M[k][:n].double().cpu().numpy() / 0.1, G[k]) < 1e-4, k

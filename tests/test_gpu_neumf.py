@@ -122,3 +122,33 @@ def test_sharded_model_at_world_1_tracks_the_ordinary_model():
     assert rel(sh.P["I"][:, :F], ref.P["I_mf"]) < 1e-5 and rel(sh.P["I"][:, F:], ref.P["I_mlp"]) < 1e-5
     for k in ("W1", "W2", "W3", "wp"):
         assert rel(sh.P[k], ref.P[k]) < 1e-5, k
+
+
+def test_train_step_wiring_is_exact_with_the_fp32_checking_gemm():
+    """Same comparison with the dense layers on the fp32 checking GEMM (ops.exact_gemm): without bf16 rounding every gradient
+    of the step agrees with the fp64 restatement to 1e-4 (fp32 accumulation) — the wiring of the 9 GEMMs, the ReLU masks, the
+    head and the embedding scatter is what the model code says, not merely "close"."""
+    nu, ni, f, B = 120, 90, 16, 700
+    with ops.exact_gemm():
+        m = NeuralMatrixFactorizationModel(nu, ni, f, 1e-3, 42, DEV)
+        for k in ("b1", "b2", "b3", "bp"):
+            m.P[k].normal_(0, 0.05)
+        for k in ("U_mf", "I_mf", "U_mlp", "I_mlp"):
+            m.P[k].mul_(4.0)
+        m._refresh()
+        P = _ref_params(m)
+        rs = np.random.RandomState(0)
+        u = rs.randint(0, nu, B).astype(np.int32); i = rs.randint(0, ni, B).astype(np.int32)
+        y = (rs.rand(B) < 0.3).astype(np.float32)
+        loss_ref, G, _ = tfm.neumf_forward_backward(P, u, i, y.astype(np.float64))
+        loss = m.train_step((torch.from_numpy(u).to(DEV), torch.from_numpy(i).to(DEV), torch.from_numpy(y).to(DEV))).item()
+    assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
+    rel = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)
+    M = lambda k: m.M[k].double().cpu().numpy() / 0.1         # first Adam step: m = 0.1 g
+    for k in ("W3", "W2", "W1"):
+        assert rel(M(k), G[k].T) < 1e-4, (k, rel(M(k), G[k].T))
+    for k, n in (("b3", f), ("b2", 2 * f), ("b1", 4 * f)):
+        assert rel(M(k)[:n], G[k]) < 1e-4, k
+    assert rel(M("wp"), G["wp"]) < 1e-4 and abs(M("bp")[0] - G["bp"]) < 1e-4 * abs(G["bp"]) + 1e-7
+    for k in ("U_mf", "I_mf", "U_mlp", "I_mlp"):
+        assert rel(M(k), G[k]) < 1e-4, (k, rel(M(k), G[k]))

@@ -57,6 +57,32 @@ def test_multidae_step_matches_restatement():
         assert not set(idx[r]) & set(rows_np[r].tolist())
 
 
+def test_multidae_wiring_is_exact_with_the_fp32_checking_gemm():
+    from elliot_b200.recommender.multi_dae import DenoisingAutoEncoder
+    nu, ni, H, L, B = 300, 1000, 64, 24, 160
+    rows_np, indptr, indices = _csr(nu, ni, 30, 0)
+    with ops.exact_gemm():
+        m = DenoisingAutoEncoder(ni, H, L, 1e-3, 0.0, 0.01, 42, indptr, indices, DEV)
+        for k in ("b1", "b2", "b3", "b4"):
+            m.P[k].normal_(0, 0.05)
+        m._refresh()
+        P = {"W1": m.P["W1"].double().cpu().numpy(), "b1": m.P["b1"][:H].double().cpu().numpy(),
+             "W2": m.P["W2"].double().cpu().numpy().T, "b2": m.P["b2"][:L].double().cpu().numpy(),
+             "W3": m.P["W3"].double().cpu().numpy().T, "b3": m.P["b3"][:H].double().cpu().numpy(),
+             "W4": m.P["W4"].double().cpu().numpy().T, "b4": m.P["b4"][:ni].double().cpu().numpy()}
+        batch = np.random.RandomState(1).choice(nu, B, replace=False).astype(np.int32)
+        X = np.zeros((B, ni))
+        for r, u in enumerate(batch):
+            X[r, rows_np[u]] = 1.0
+        loss_ref, G, logits_ref = tfm.multidae_forward_backward(P, X)
+        loss = m.train_step(torch.from_numpy(batch).to(DEV), 0.0)
+    assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
+    for k, tr in (("W4", True), ("W3", True), ("W2", True), ("W1", False)):
+        assert rel(m.M[k].double().cpu().numpy() / 0.1, G[k].T if tr else G[k]) < 1e-4, k
+    for k, n in (("b4", ni), ("b3", H), ("b2", L), ("b1", H)):
+        assert rel(m.M[k][:n].double().cpu().numpy() / 0.1, G[k]) < 1e-4, k
+
+
 def test_gmf_fused_step_matches_restatement():
     """fp32 CUDA-core kernel vs the fp64 restatement: loss 1e-6, every gradient 1e-5 relative (no bf16 anywhere)."""
     from elliot_b200.recommender.gmf import GeneralizedMatrixFactorizationModel
