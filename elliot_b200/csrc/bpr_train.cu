@@ -263,14 +263,15 @@ __global__ void __launch_bounds__(256) bpr_hogwild_kernel(const HogwildParams p)
 // register cost, the groups then read the rows from shared memory (conflict-free 128-bit loads).  That is the
 // "128-bit row loads staged through shared memory" layout of the north_star, and it is what lets rows that live in a
 // PEER GPU's memory (PEER mode: 2-3x the latency of local HBM) arrive without stalling the arithmetic.
-// TT rows-triples per warp chunk: 12 KB of shared memory per warp whatever the row length (DP = 32/64/128 floats).
-template <int DP, bool SAMPLE, bool PEER>
+// TT rows-triples per warp chunk: 12 KB of shared memory per warp whatever the row length (DP = 32/64/128 floats); halving the
+// chunk to fit 4 CTAs per SM was measured SLOWER (1.32 vs 1.01 ms at C2): the step is not short of resident warps.
+template <int DP, bool SAMPLE, bool PEER, int CHUNK_BYTES = 4096>
 __global__ void __launch_bounds__(256) bpr_hogwild_stage_kernel(const HogwildParams p) {
     constexpr int NV = DP / 4;                 // float4 per row
     constexpr int G = NV >= 32 ? 32 : NV;      // lanes per triple
     constexpr int VPL = NV / G;                // float4 per lane
     constexpr int ROWB = DP * 4;
-    constexpr int TT = 4096 / ROWB;            // triples per chunk (32 / 16 / 8)
+    constexpr int TT = CHUNK_BYTES / ROWB;     // triples per chunk (32 / 16 / 8 at 4 KB of rows per row kind)
     constexpr int NGRP = 32 / G;               // triples processed side by side
     static_assert(TT >= NGRP && TT <= 32 && 32 % TT == 0, "chunk shape");
     extern __shared__ __align__(128) uint8_t stage_smem[];
@@ -418,10 +419,10 @@ __global__ void __launch_bounds__(256) bpr_hogwild_stage_kernel(const HogwildPar
     }
 }
 
-template <int DP, bool SAMPLE, bool PEER>
+template <int DP, bool SAMPLE, bool PEER, int CHUNK_BYTES = 4096>
 static int launch_stage_t(const HogwildParams &p, int reserve_sms, cudaStream_t st) {
-    constexpr int SMEM = 8 * 12288 + 64;                   // 8 warps x 12 KB + mbarriers
-    auto kern = bpr_hogwild_stage_kernel<DP, SAMPLE, PEER>;
+    constexpr int SMEM = 8 * 3 * CHUNK_BYTES + 64;         // 8 warps x 3 row kinds x chunk + mbarriers
+    auto kern = bpr_hogwild_stage_kernel<DP, SAMPLE, PEER, CHUNK_BYTES>;
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int per_sm = 0;
     EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, SMEM));
