@@ -50,6 +50,7 @@ SIGNATURES = {
     "eb_bpr_batch_grad_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void, c_void, c_void,
                                       c_i64, c_f32, c_f32, c_void, c_void]),
     "eb_adam_dense_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_void]),
+    "eb_adam_dense_copy_f32": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_i64, c_void, c_void]),
     "eb_convert_bf16": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_i64, c_int, c_void]),
     "eb_gemm_bf16_tn": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
                                 c_void]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "eb_vae_reparam_fwd": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_i64, c_u64, c_u64, c_void, c_void]),
     "eb_vae_reparam_bwd": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_i64, c_void, c_i64, c_u64, c_u64, c_f32, c_void]),
     "eb_vae_softmax": (c_int, [c_void, c_i64, c_int, c_void, c_void, c_void, c_int, c_void, c_void, c_int, c_void]),
+    "eb_vae_softmax_bf16": (c_int, [c_void, c_i64, c_int, c_void, c_void, c_void, c_int, c_void, c_void, c_int, c_void, c_i64, c_void]),
     "eb_tanh_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_colsum": (c_int, [c_void, c_int, c_int, c_i64, c_void, c_void]),
     "eb_dense_topk_f32": (c_int, [c_void, c_i64, c_int, c_int, c_void, c_void, c_void, c_void, c_int, c_void, c_void, c_void]),

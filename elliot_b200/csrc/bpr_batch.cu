@@ -12,6 +12,8 @@
 // (2) one streaming dense Adam pass per table that also clears the gradient.
 // tensorflow==2.3.2 cannot be executed in the build container: parity with TF is UNPINNED; the
 // checker is the numpy restatement oracle/tf_models.py::bprmf_batch_step.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace eb {
@@ -108,7 +110,8 @@ __global__ void __launch_bounds__(256, 4) bpr_batch_grad_kernel(const BatchGradP
 // Keras Adam, dense form (what TF 2.3 does to every row of a variable even for sparse grads)
 __global__ void __launch_bounds__(256) adam_dense_kernel(float *__restrict__ var, float *__restrict__ m,
                                                          float *__restrict__ v, float *__restrict__ grad, int64_t n4,
-                                                         float b1, float b2, float lr_t, float eps) {
+                                                         float b1, float b2, float lr_t, float eps,
+                                                         __nv_bfloat162 *__restrict__ copy_bf16) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
@@ -122,6 +125,10 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(float *__restrict__ var
         x.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); x.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
         reinterpret_cast<float4 *>(m)[i] = mm; reinterpret_cast<float4 *>(v)[i] = vv;
         reinterpret_cast<float4 *>(var)[i] = x;
+        if (copy_bf16) {                               // the tensor-core operand copy of the new weights, same layout
+            copy_bf16[2 * i] = __floats2bfloat162_rn(x.x, x.y);
+            copy_bf16[2 * i + 1] = __floats2bfloat162_rn(x.z, x.w);
+        }
         reinterpret_cast<float4 *>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -157,13 +164,20 @@ extern "C" int eb_bpr_batch_grad_f32(const float *Gu, const float *Gi, const flo
 
 extern "C" int eb_adam_dense_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
                                  float eps, int64_t step, void *stream) {
+    return eb_adam_dense_copy_f32(var, m, v, grad, n, lr, beta1, beta2, eps, step, nullptr, stream);
+}
+
+extern "C" int eb_adam_dense_copy_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
+                                      float eps, int64_t step, void *copy_bf16, void *stream) {
     EB_ARG(var && m && v && grad && n >= 0 && (n % 4) == 0 && step >= 1, "bad argument (n must be a multiple of 4, step >= 1)");
+    EB_ARG(!copy_bf16 || ((uintptr_t)copy_bf16 % 4) == 0, "bf16 copy must be 4-byte aligned");
     if (n == 0) return EB_OK;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
     int64_t grid = (n / 4 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
-    adam_dense_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(var, m, v, grad, n / 4, beta1, beta2, (float)lr_t, eps);
+    adam_dense_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(var, m, v, grad, n / 4, beta1, beta2, (float)lr_t, eps,
+                                                                        (__nv_bfloat162 *)copy_bf16);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

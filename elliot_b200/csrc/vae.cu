@@ -14,6 +14,8 @@
 // the build container: parity with TF is UNPINNED; checker = oracle/tf_models.py (fp64 numpy).
 #include <math_constants.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace eb {
@@ -161,6 +163,74 @@ __global__ void __launch_bounds__(256) vae_softmax_kernel(float *__restrict__ lo
     for (int64_t p = beg + threadIdx.x; p < end; p += blockDim.x) row[indices[p]] -= invB;
 }
 
+// The same with the row staged in shared memory: ONE read of the row from HBM/L2 (128-bit loads), max / sum-exp / gradient
+// from shared memory, the gradient written once as fp32 (for the bias column sums) and, optionally, as the bf16 operand
+// copy the backward GEMMs read (so no separate conversion pass over the B x I block).  n_items * 4 bytes must fit the
+// dynamic shared memory given at launch; row starts must be 16-byte aligned (ld % 4 == 0).
+__global__ void __launch_bounds__(512) vae_softmax_smem_kernel(float *__restrict__ logits, int64_t ld, int n_items,
+                                                               const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                                               const int32_t *__restrict__ rows, int B, double *nll_sum, float *lse_out,
+                                                               int write_grad, __nv_bfloat16 *__restrict__ grad_bf16, int64_t ldb) {
+    extern __shared__ __align__(16) float srow[];
+    __shared__ float red[16];
+    __shared__ float s_bcast;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float *row = logits + (int64_t)b * ld;
+    const int n4 = n_items >> 2;
+    float m = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4 *>(row)[i];
+        reinterpret_cast<float4 *>(srow)[i] = v;
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n_items; i += blockDim.x) { const float v = row[i]; srow[i] = v; m = fmaxf(m, v); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = red[0]; for (int w = 1; w < nwarp; w++) t = fmaxf(t, red[w]); s_bcast = t; }
+    __syncthreads();
+    m = s_bcast;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) s += __expf(srow[i] - m);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < nwarp; w++) t += red[w]; s_bcast = m + __logf(t); }
+    __syncthreads();
+    const float lse = s_bcast;
+    if (lse_out && threadIdx.x == 0) lse_out[b] = lse;
+    const int u = rows[b];
+    const int64_t beg = indptr[u], end = indptr[u + 1];
+    if (nll_sum) {
+        float a = 0.f;
+        for (int64_t p = beg + threadIdx.x; p < end; p += blockDim.x) a += srow[indices[p]] - lse;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0 && a != 0.f) atomicAdd(nll_sum, -(double)a);
+    }
+    if (!write_grad) return;
+    __syncthreads();
+    const float nb = (float)(end - beg), invB = 1.f / (float)B;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) srow[i] = __expf(srow[i] - lse) * nb * invB;
+    __syncthreads();
+    for (int64_t p = beg + threadIdx.x; p < end; p += blockDim.x) srow[indices[p]] -= invB;
+    __syncthreads();
+    __nv_bfloat16 *brow = grad_bf16 ? grad_bf16 + (int64_t)b * ldb : nullptr;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4 *>(srow)[i];
+        reinterpret_cast<float4 *>(row)[i] = v;
+        if (brow) {
+            reinterpret_cast<__nv_bfloat162 *>(brow)[2 * i] = __floats2bfloat162_rn(v.x, v.y);
+            reinterpret_cast<__nv_bfloat162 *>(brow)[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+        }
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n_items; i += blockDim.x) { row[i] = srow[i]; if (brow) brow[i] = __float2bfloat16_rn(srow[i]); }
+    if (brow) for (int64_t i = n_items + threadIdx.x; i < ldb; i += blockDim.x) brow[i] = __float2bfloat16_rn(0.f);   // padding columns
+}
+
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ out,
                                                        float *__restrict__ dpre, int64_t n) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -280,12 +350,31 @@ extern "C" int eb_vae_reparam_bwd(const float *ml, int64_t ldml, int B, int L, c
     return EB_OK;
 }
 
-extern "C" int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
-                              const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *stream) {
+extern "C" int eb_vae_softmax_bf16(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
+                                   const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *grad_bf16,
+                                   int64_t ld_bf16, void *stream) {
     EB_ARG(logits && indptr && indices && rows && B >= 1 && n_items >= 1 && ld >= n_items, "bad argument");
-    vae_softmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld, n_items, indptr, indices, rows, B, nll_sum, lse_out, write_grad);
+    EB_ARG(!grad_bf16 || (write_grad && ld_bf16 >= n_items && ld_bf16 % 2 == 0 && ((uintptr_t)grad_bf16 % 4) == 0), "bad bf16 gradient buffer");
+    const size_t smem = (size_t)n_items * sizeof(float);
+    const bool staged = smem <= 200 * 1024 && ld % 4 == 0 && ((uintptr_t)logits % 16) == 0;
+    if (staged) {
+        EB_CUDA(cudaFuncSetAttribute(vae_softmax_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        vae_softmax_smem_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(logits, ld, n_items, indptr, indices, rows, B, nll_sum, lse_out,
+                                                                        write_grad, (__nv_bfloat16 *)grad_bf16, ld_bf16);
+    } else {
+        vae_softmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld, n_items, indptr, indices, rows, B, nll_sum, lse_out, write_grad);
+        if (grad_bf16) {
+            EB_CUDA(cudaGetLastError());
+            return eb_convert_bf16(logits, B, n_items, ld, grad_bf16, ld_bf16, 0, stream);
+        }
+    }
     EB_CUDA(cudaGetLastError());
     return EB_OK;
+}
+
+extern "C" int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
+                              const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *stream) {
+    return eb_vae_softmax_bf16(logits, ld, n_items, indptr, indices, rows, B, nll_sum, lse_out, write_grad, nullptr, 0, stream);
 }
 
 extern "C" int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream) {

@@ -74,8 +74,7 @@ extern "C" int eb_vae_train_step(const eb_vae_model *m, const int32_t *rows, int
         // ---- loss + backward (multi_vae_model.py:114-142); dlogits overwrite the logits.  Every backward GEMM reads the row-major
         // bf16 copies as they lie: "rows are K" operands (eb_gemm_bf16) instead of transposed copies — dW = dY^T . X contracts over
         // the batch rows of both operands, dX = dY . W takes the [out][in] weight as a [K][N] matrix.
-        EB_TRY(eb_vae_softmax(w.logits, I, (int)I, m->indptr, m->indices, rows, B, acc + 1, nullptr, 1, stream));
-        EB_TRY(eb_convert_bf16(w.logits, B, (int)I, I, w.dlb, I8, 0, stream));
+        EB_TRY(eb_vae_softmax_bf16(w.logits, I, (int)I, m->indptr, m->indices, rows, B, acc + 1, nullptr, 1, w.dlb, I8, stream));
         EB_TRY(eb_gemm_bf16(w.dlb, I8, 1, w.h2b, H8, 1, m->gW4, H, (int)I, (int)H, B, nullptr, 1.f, 0, stream));
         EB_TRY(eb_colsum(w.logits, B, (int)I, I, m->gb4, stream));
         EB_TRY(eb_gemm_bf16(w.dlb, I8, 0, m->W4b, H8, 1, w.dh2, H, B, (int)H, (int)I, nullptr, 1.f, 0, stream));
@@ -98,16 +97,18 @@ extern "C" int eb_vae_train_step(const eb_vae_model *m, const int32_t *rows, int
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f;
         EB_TRY(eb_adam_dense_f32(m->W1, m->mW1, m->vW1, m->gW1, I * H, lr, b1, b2, eps, (int64_t)step, stream));
         EB_TRY(eb_adam_dense_f32(m->b1, m->mb1, m->vb1, m->gb1, pad4(H), lr, b1, b2, eps, (int64_t)step, stream));
-        EB_TRY(eb_adam_dense_f32(m->W2, m->mW2, m->vW2, m->gW2, 2 * L * H, lr, b1, b2, eps, (int64_t)step, stream));
+        // kernels whose row length is a multiple of 8 get their bf16 operand copy straight from the optimiser pass
+        const bool c2 = H % 8 == 0, c3 = L % 8 == 0;
+        EB_TRY(eb_adam_dense_copy_f32(m->W2, m->mW2, m->vW2, m->gW2, 2 * L * H, lr, b1, b2, eps, (int64_t)step, c2 ? m->W2b : nullptr, stream));
         EB_TRY(eb_adam_dense_f32(m->b2, m->mb2, m->vb2, m->gb2, pad4(2 * L), lr, b1, b2, eps, (int64_t)step, stream));
-        EB_TRY(eb_adam_dense_f32(m->W3, m->mW3, m->vW3, m->gW3, H * L, lr, b1, b2, eps, (int64_t)step, stream));
+        EB_TRY(eb_adam_dense_copy_f32(m->W3, m->mW3, m->vW3, m->gW3, H * L, lr, b1, b2, eps, (int64_t)step, c3 ? m->W3b : nullptr, stream));
         EB_TRY(eb_adam_dense_f32(m->b3, m->mb3, m->vb3, m->gb3, pad4(H), lr, b1, b2, eps, (int64_t)step, stream));
-        EB_TRY(eb_adam_dense_f32(m->W4, m->mW4, m->vW4, m->gW4, I * H, lr, b1, b2, eps, (int64_t)step, stream));
+        EB_TRY(eb_adam_dense_copy_f32(m->W4, m->mW4, m->vW4, m->gW4, I * H, lr, b1, b2, eps, (int64_t)step, c2 ? m->W4b : nullptr, stream));
         EB_TRY(eb_adam_dense_f32(m->b4, m->mb4, m->vb4, m->gb4, pad4(I), lr, b1, b2, eps, (int64_t)step, stream));
         const int64_t H8 = pad8(H), L8 = pad8(L), LL = 2 * L;
-        EB_TRY(eb_convert_bf16(m->W2, (int)LL, (int)H, H, m->W2b, H8, 0, stream));
-        EB_TRY(eb_convert_bf16(m->W3, (int)H, (int)L, L, m->W3b, L8, 0, stream));
-        EB_TRY(eb_convert_bf16(m->W4, (int)I, (int)H, H, m->W4b, H8, 0, stream));
+        if (!c2) EB_TRY(eb_convert_bf16(m->W2, (int)LL, (int)H, H, m->W2b, H8, 0, stream));
+        if (!c3) EB_TRY(eb_convert_bf16(m->W3, (int)H, (int)L, L, m->W3b, L8, 0, stream));
+        if (!c2) EB_TRY(eb_convert_bf16(m->W4, (int)I, (int)H, H, m->W4b, H8, 0, stream));
     }
     return EB_OK;
 }

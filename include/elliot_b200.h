@@ -186,6 +186,10 @@ int eb_bpr_batch_grad_f32(const float *Gu, const float *Gi, const float *Bi, flo
                           float l_w, float l_b, double *loss, void *stream);
 int eb_adam_dense_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
                       float eps, int64_t step, void *stream);
+/* the same, also writing the updated values as a bf16 array of the same length and layout (the tensor-core operand copy of a
+ * dense kernel whose row length is a multiple of 8: no separate conversion pass after the optimiser) */
+int eb_adam_dense_copy_f32(float *var, float *m, float *v, float *grad, int64_t n, float lr, float beta1, float beta2,
+                           float eps, int64_t step, void *copy_bf16, void *stream);
 
 /* ------------------------------------------------------------------------
  * MultiVAE pieces around the dense layers (multi_vae_model.py:20-159, sparse_sampler.py:13-25).
@@ -202,6 +206,11 @@ int eb_vae_reparam_bwd(const float *ml, int64_t ldml, int B, int L, const float 
                        int64_t lddml, uint64_t seed, uint64_t step, float anneal, void *stream);
 int eb_vae_softmax(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
                    const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *stream);
+/* the same, additionally writing the gradient as bf16 rows (row stride ld_bf16 >= n_items, padding columns zeroed): the operand
+ * copy the backward GEMMs read.  Rows up to 200 KB are staged in shared memory (one pass over the B x I block). */
+int eb_vae_softmax_bf16(float *logits, int64_t ld, int n_items, const int64_t *indptr, const int32_t *indices,
+                        const int32_t *rows, int B, double *nll_sum, float *lse_out, int write_grad, void *grad_bf16,
+                        int64_t ld_bf16, void *stream);
 int eb_tanh_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
 int eb_colsum(const float *src, int rows, int cols, int64_t ld, float *out, void *stream);
 /* One whole MultiVAE training step as ONE native call: the same kernels as the entry points above, issued back to back
