@@ -56,6 +56,8 @@ SIGNATURES = {
                                 c_void]),
     "eb_gemm_bf16": (c_int, [c_void, c_i64, c_int, c_void, c_i64, c_int, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
                              c_void]),
+    "eb_gemm_bf16_out": (c_int, [c_void, c_i64, c_int, c_void, c_i64, c_int, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_void,
+                                 c_f32, c_int, c_void]),
     "eb_gemm_f32_ref": (c_int, [c_void, c_i64, c_int, c_void, c_i64, c_int, c_void, c_i64, c_int, c_int, c_int, c_void, c_f32, c_int,
                                 c_void]),
     "eb_vae_embed_fwd": (c_int, [c_void, c_void, c_int, c_void, c_void, c_void, c_int, c_void, c_i64, c_f32, c_u64, c_void]),
@@ -72,6 +74,7 @@ SIGNATURES = {
                               c_void, c_void, c_void]),
     "eb_neumf_head_norm": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void,
                                    c_void, c_void, c_void, c_void]),
+    "eb_relu_bwd_copy": (c_int, [c_void, c_void, c_void, c_i64, c_void, c_void]),
     "eb_relu_bwd": (c_int, [c_void, c_void, c_void, c_i64, c_void]),
     "eb_neumf_scatter": (c_int, [c_void, c_void, c_int, c_i64, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_void,
                                  c_void, c_void, c_void]),

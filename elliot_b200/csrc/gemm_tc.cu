@@ -36,6 +36,8 @@ struct GemmParams {
     float alpha;         // C = alpha * (A B^T) + bias, then activation
     int splits;          // split-K factor: > 1 -> each work item covers a K range and ADDS into a zeroed C (no bias/act)
     int tma_store;       // 1: epilogue through shared memory + TMA store / reduce (tmC valid); 0: direct row-per-lane stores
+    __nv_bfloat16 *Cb;   // optional second output: the same values as bf16 rows (row stride ldcb) — the next layer's operand copy
+    int64_t ldcb;
 };
 
 // A_MN / B_MN: the operand is given with its M (resp. N) index contiguous — a [K][M] row-major matrix — instead of K-major.
@@ -170,6 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t box = smem_u32(epi + (quad * 2 + (chunk & 1)) * G_EPI_BOX);
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box used 2 chunks ago is read
                         __syncwarp();
+                        const int my_row = tm * G_BM + quad * 32 + lane;
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             float4 o = make_float4(p.alpha * __uint_as_float(r[c]), p.alpha * __uint_as_float(r[c + 1]),
@@ -184,6 +187,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             const uint32_t dst = box + (uint32_t)lane * 128u + (uint32_t)(((c >> 2) ^ (lane & 7)) << 4);
                             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                            if (p.Cb && my_row < p.M) {                 // bf16 copy of the same values, straight from the registers
+                                __nv_bfloat16 *cb = p.Cb + (int64_t)my_row * p.ldcb + col0 + c;
+                                if (col0 + c + 4 <= p.N && (p.ldcb & 3) == 0) {
+                                    const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                                    uint2 pk;
+                                    pk.x = *reinterpret_cast<const uint32_t *>(&lo); pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                                    *reinterpret_cast<uint2 *>(cb) = pk;
+                                } else {
+                                    const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; e++)
+                                        if (col0 + c + e < p.N) cb[e] = __float2bfloat16_rn(ov[e]);
+                                }
+                            }
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
                         __syncwarp();
@@ -343,7 +360,8 @@ extern "C" int eb_convert_bf16(const float *src, int rows, int cols, int64_t ld,
 }
 
 static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_bf16, int64_t ldb, bool b_mn, float *C, int64_t ldc,
-                     int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
+                     int M, int N, int K, const float *bias, float alpha, int act, void *stream, void *C_bf16 = nullptr,
+                     int64_t ldcb = 0) {
     EB_ARG(A_bf16 && B_bf16 && C, "null pointer");
     EB_ARG(M >= 1 && N >= 1 && K >= 1 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldc >= N, "bad shape M=%d N=%d K=%d", M, N, K);
     EB_ARG(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb must be multiples of 8 bf16 (16-byte TMA strides)");
@@ -355,6 +373,7 @@ static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_b
     // TMA needs a 16-byte aligned base and row stride; otherwise (and with EB_GEMM_TMA_STORE=0) the direct-store epilogue runs
     static const bool tma_off = [] { const char *e = getenv("EB_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
     const bool tma_store = !tma_off && (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
+    EB_ARG(!C_bf16 || (tma_store && ldcb >= N && ((uintptr_t)C_bf16 % 8) == 0), "the bf16 second output needs the TMA-store epilogue (16-byte aligned C, ldc % 4 == 0)");
     if (tma_store) { if (int rc = g_make_map_c(&mc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc)) return rc; }
     else mc = ma;
     const int n_out_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
@@ -362,14 +381,14 @@ static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_b
     // split-K: few output tiles with a long K (dh2 = dlogits . W4: 20 tiles, K = 26 744) leave most SMs idle and each
     // busy CTA load-latency bound; split the K range over the idle SMs and add the partial tiles into a zeroed C
     int splits = 1;
-    if (!bias && act == 0 && n_out_tiles * 2 <= sm_count() && k_blocks >= 16) {
+    if (!bias && act == 0 && !C_bf16 && n_out_tiles * 2 <= sm_count() && k_blocks >= 16) {
         splits = sm_count() / n_out_tiles;
         if (splits > k_blocks / 8) splits = k_blocks / 8;           // at least 8 k-blocks per work item
         if (splits < 1) splits = 1;
         const int per = (k_blocks + splits - 1) / splits;
         splits = (k_blocks + per - 1) / per;                         // no empty trailing splits
     }
-    GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits, tma_store ? 1 : 0};
+    GemmParams p{C, ldc, bias, M, N, K, act, alpha, splits, tma_store ? 1 : 0, (__nv_bfloat16 *)C_bf16, ldcb};
     if (splits > 1) {
         if (ldc == N) EB_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream));
         else EB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, (cudaStream_t)stream));
@@ -399,4 +418,10 @@ extern "C" int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf
 extern "C" int eb_gemm_bf16(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
                             float *C, int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream) {
     return gemm_bf16(A_bf16, lda, a_rows_are_k != 0, B_bf16, ldb, b_rows_are_k != 0, C, ldc, M, N, K, bias, alpha, act, stream);
+}
+
+extern "C" int eb_gemm_bf16_out(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
+                                float *C, int64_t ldc, void *C_bf16, int64_t ldcb, int M, int N, int K, const float *bias, float alpha,
+                                int act, void *stream) {
+    return gemm_bf16(A_bf16, lda, a_rows_are_k != 0, B_bf16, ldb, b_rows_are_k != 0, C, ldc, M, N, K, bias, alpha, act, stream, C_bf16, ldcb);
 }

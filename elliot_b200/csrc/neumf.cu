@@ -93,9 +93,12 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *pm, int64_
     }
 }
 
-__global__ void __launch_bounds__(256) relu_bwd_kernel(const float *dout, const float *out, float *dpre, int64_t n) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
-        dpre[e] = out[e] > 0.f ? dout[e] : 0.f;
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float *dout, const float *out, float *dpre, int64_t n, __nv_bfloat16 *copy) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float d = out[e] > 0.f ? dout[e] : 0.f;
+        dpre[e] = d;
+        if (copy) copy[e] = __float2bfloat16_rn(d);          // the operand copy the next two GEMMs read (row length % 8 == 0: same layout)
+    }
 }
 
 __global__ void __launch_bounds__(256) neumf_scatter_kernel(const float *Umf, const float *Imf, int f, int64_t ldt, const int32_t *u,
@@ -215,12 +218,16 @@ extern "C" int eb_neumf_head(const float *pm, int64_t ldp, const float *h3, int6
     return eb_neumf_head_norm(pm, ldp, h3, ldh, f, wp, bp, label, n, n > 0 ? n : 1, dpm, dh3, dwp, dbp, loss, prob_out, stream);
 }
 
-extern "C" int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream) {
+extern "C" int eb_relu_bwd_copy(const float *dout, const float *out, float *dpre, int64_t n, void *copy_bf16, void *stream) {
     EB_ARG(dout && out && dpre && n >= 0, "bad argument");
     if (n == 0) return EB_OK;
-    relu_bwd_kernel<<<ngrid(n), 256, 0, (cudaStream_t)stream>>>(dout, out, dpre, n);
+    relu_bwd_kernel<<<ngrid(n), 256, 0, (cudaStream_t)stream>>>(dout, out, dpre, n, (__nv_bfloat16 *)copy_bf16);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
+}
+
+extern "C" int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream) {
+    return eb_relu_bwd_copy(dout, out, dpre, n, nullptr, stream);
 }
 
 extern "C" int eb_neumf_scatter(const float *Umf, const float *Imf, int f, int64_t ldt, const int32_t *u, const int32_t *it, int64_t n,

@@ -336,11 +336,23 @@ def to_bf16(src, transpose=False, out=None):
     return out
 
 
-def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None):
-    """C[M][N] fp32 = act(alpha * A[M][:K] @ B[N][:K]^T + bias) on the tensor cores (A, B bf16, K-major)."""
+def gemm_bf16_tn(A, B, M, N, K, bias=None, alpha=1.0, act=0, out=None, out_bf16=False):
+    """C[M][N] fp32 = act(alpha * A[M][:K] @ B[N][:K]^T + bias) on the tensor cores (A, B bf16, K-major).
+    out_bf16=True: returns (C, C_bf16) — the bf16 operand copy of C written by the epilogue itself (no conversion pass)."""
     _need_cuda(A, B, bias, out)
     if A.dtype == torch.float32:                          # exact_gemm checking mode
-        return _gemm_ref(A, B, M, N, K, False, False, bias, alpha, act, out)
+        C = _gemm_ref(A, B, M, N, K, False, False, bias, alpha, act, out)
+        return (C, C) if out_bf16 else C
+    if out_bf16:
+        assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        ldb = (N + 7) // 8 * 8
+        Cb = torch.empty((M, ldb), dtype=torch.bfloat16, device=A.device) if ldb == N else torch.zeros((M, ldb), dtype=torch.bfloat16, device=A.device)
+        with torch.cuda.device(A.device):
+            check(lib().eb_gemm_bf16_out(_ptr(A), A.stride(0), 0, _ptr(B), B.stride(0), 0, _ptr(out), out.stride(0), _ptr(Cb), ldb,
+                                         M, N, K, _ptr(bias), alpha, act, _stream(A)))
+        return out, Cb
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
@@ -497,11 +509,17 @@ def neumf_head(pm, h3, f, wp, bp, label=None, dpm=None, dh3=None, dwp=None, dbp=
           int(mean_over) if mean_over else max(int(pm.shape[0]), 1), _ptr(dpm), _ptr(dh3), _ptr(dwp), _ptr(dbp), _ptr(loss), _ptr(prob))
 
 
-def relu_bwd(dout, out):
+def relu_bwd(dout, out, copy_bf16=False):
+    """dpre = dout * (out > 0); copy_bf16=True also returns dpre's bf16 operand copy, written in the same pass (row length % 8 == 0)."""
     _need_cuda(dout, out)
     dpre = torch.empty_like(dout)
+    if copy_bf16 and not _EXACT_GEMM:
+        assert dout.dim() == 2 and dout.shape[1] % 8 == 0 and dout.is_contiguous()
+        cb = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
+        _call("eb_relu_bwd_copy", dout, _ptr(dout), _ptr(out), _ptr(dpre), dout.numel(), _ptr(cb))
+        return dpre, cb
     _call("eb_relu_bwd", dout, _ptr(dout), _ptr(out), _ptr(dpre), dout.numel())
-    return dpre
+    return (dpre, dpre) if copy_bf16 else dpre
 
 
 def neumf_scatter(Umf, Imf, f, u, it, dpm, dx0, dUmf, dImf, dUmlp, dImlp):

@@ -98,8 +98,9 @@ class ShardedNeuMFModel:
     def _mlp(self, x0):
         f, B = self.f, x0.shape[0]
         x0b = ops.to_bf16(x0)
-        h1 = ops.gemm_bf16_tn(x0b, self.Wb["W1"], B, 4 * f, 2 * f, bias=self.P["b1"], act=2); h1b = ops.to_bf16(h1)
-        h2 = ops.gemm_bf16_tn(h1b, self.Wb["W2"], B, 2 * f, 4 * f, bias=self.P["b2"], act=2); h2b = ops.to_bf16(h2)
+        # each layer's epilogue writes the bf16 operand copy of its output beside the fp32 activations
+        h1, h1b = ops.gemm_bf16_tn(x0b, self.Wb["W1"], B, 4 * f, 2 * f, bias=self.P["b1"], act=2, out_bf16=True)
+        h2, h2b = ops.gemm_bf16_tn(h1b, self.Wb["W2"], B, 2 * f, 4 * f, bias=self.P["b2"], act=2, out_bf16=True)
         h3 = ops.gemm_bf16_tn(h2b, self.Wb["W3"], B, f, 2 * f, bias=self.P["b3"], act=2)
         self._act_b = (x0b, h1b, h2b)                     # row-major bf16 copies, read again ("rows are K") by the weight-gradient GEMMs
         return h1, h2, h3
@@ -123,11 +124,9 @@ class ShardedNeuMFModel:
         x0b, h1b, h2b = self._act_b
         d3b = ops.to_bf16(dpre3)
         ops.gemm_bf16(d3b, h2b, f, 2 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W3"]); ops.colsum(dpre3, G["b3"])
-        dpre2 = ops.relu_bwd(ops.gemm_bf16(d3b, self.Wb["W3"], B, 2 * f, f, b_rows_are_k=True), h2)
-        d2b = ops.to_bf16(dpre2)
+        dpre2, d2b = ops.relu_bwd(ops.gemm_bf16(d3b, self.Wb["W3"], B, 2 * f, f, b_rows_are_k=True), h2, copy_bf16=True)
         ops.gemm_bf16(d2b, h1b, 2 * f, 4 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W2"]); ops.colsum(dpre2, G["b2"])
-        dpre1 = ops.relu_bwd(ops.gemm_bf16(d2b, self.Wb["W2"], B, 4 * f, 2 * f, b_rows_are_k=True), h1)
-        d1b = ops.to_bf16(dpre1)
+        dpre1, d1b = ops.relu_bwd(ops.gemm_bf16(d2b, self.Wb["W2"], B, 4 * f, 2 * f, b_rows_are_k=True), h1, copy_bf16=True)
         ops.gemm_bf16(d1b, x0b, 4 * f, 2 * f, B, a_rows_are_k=True, b_rows_are_k=True, out=G["W1"]); ops.colsum(dpre1, G["b1"])
         dx0 = ops.gemm_bf16(d1b, self.Wb["W1"], B, 2 * f, 4 * f, b_rows_are_k=True)
         ops.neumf_scatter_peer(P["U_mf"], I.ptrs, GI.ptrs, I.shard_rows, 2 * f, f, u, it, dpm, dx0, G["U_mf"], G["U_mlp"])

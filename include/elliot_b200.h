@@ -256,6 +256,8 @@ int eb_neumf_head_norm(const float *pm, int64_t ldp, const float *h3, int64_t ld
                        const float *label, int64_t n, int64_t mean_over, float *dpm, float *dh3, float *dwp, float *dbp,
                        double *loss, float *prob_out, void *stream);
 int eb_relu_bwd(const float *dout, const float *out, float *dpre, int64_t n, void *stream);
+/* the same, also writing dpre as a bf16 array of the same length (operand copy; row length a multiple of 8) */
+int eb_relu_bwd_copy(const float *dout, const float *out, float *dpre, int64_t n, void *copy_bf16, void *stream);
 int eb_neumf_scatter(const float *Umf, const float *Imf, int f, int64_t ldt, const int32_t *u, const int32_t *it, int64_t n,
                      const float *dpm, int64_t ldp, const float *dx0, int64_t ldx, float *dUmf, float *dImf, float *dUmlp,
                      float *dImlp, void *stream);
@@ -347,6 +349,11 @@ int eb_gemm_bf16_tn(const void *A_bf16, int64_t lda, const void *B_bf16, int64_t
  * descriptors), so the backward GEMMs dW = dY^T . X (K = batch) and dX = dY . W with W kept [K][N] need no transposed copies. */
 int eb_gemm_bf16(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
                  float *C, int64_t ldc, int M, int N, int K, const float *bias, float alpha, int act, void *stream);
+/* ... and with a second output: C_bf16 (row stride ldcb >= N) receives the same values as bf16 — the next layer's operand copy,
+ * written from the epilogue's registers instead of by a conversion pass (not combined with split-K). */
+int eb_gemm_bf16_out(const void *A_bf16, int64_t lda, int a_rows_are_k, const void *B_bf16, int64_t ldb, int b_rows_are_k,
+                     float *C, int64_t ldc, void *C_bf16, int64_t ldcb, int M, int N, int K, const float *bias, float alpha,
+                     int act, void *stream);
 /* CHECKING path (tests only, slow): the same contraction with fp32 operands on the CUDA cores, fixed-order fp32 FMA
  * accumulation — lets the dense-layer models be compared with their fp64 restatements to 1e-5 instead of bf16's 1e-2. */
 int eb_gemm_f32_ref(const float *A, int64_t lda, int a_rows_are_k, const float *B, int64_t ldb, int b_rows_are_k, float *C,

@@ -56,3 +56,13 @@ def test_gemm_with_rows_are_k_operands(M, N, K, a_mn, b_mn):
     ref = 0.5 * (A.bfloat16().double() @ B.bfloat16().double().T)
     tol = 2e-4 if K < 100000 else 2e-3                                       # split-K atomics over 1M products
     assert (C.double() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 256, 128, 2), (130, 70, 200, 0), (512, 600, 600, 1)])
+def test_gemm_second_output_is_the_bf16_copy(M, N, K, act):
+    g = torch.Generator(device=DEV); g.manual_seed(M + N)
+    A = torch.randn(M, K, device=DEV, generator=g) / K ** 0.5; B = torch.randn(N, K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    C, Cb = ops.gemm_bf16_tn(ops.to_bf16(A), ops.to_bf16(B), M, N, K, bias=bias, act=act, out_bf16=True)
+    C2 = ops.gemm_bf16_tn(ops.to_bf16(A), ops.to_bf16(B), M, N, K, bias=bias, act=act)
+    assert torch.equal(C, C2) and torch.equal(Cb[:, :N], C.bfloat16()) and not Cb[:, N:].any()
