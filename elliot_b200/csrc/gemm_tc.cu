@@ -373,7 +373,11 @@ static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_b
     // TMA needs a 16-byte aligned base and row stride; otherwise (and with EB_GEMM_TMA_STORE=0) the direct-store epilogue runs
     static const bool tma_off = [] { const char *e = getenv("EB_GEMM_TMA_STORE"); return e && e[0] == '0'; }();
     const bool tma_store = !tma_off && (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
-    EB_ARG(!C_bf16 || (tma_store && ldcb >= N && ((uintptr_t)C_bf16 % 8) == 0), "the bf16 second output needs the TMA-store epilogue (16-byte aligned C, ldc % 4 == 0)");
+    EB_ARG(!C_bf16 || (ldcb >= N && ldcb % 8 == 0 && ((uintptr_t)C_bf16 % 8) == 0), "bf16 second output: ldcb must be a multiple of 8 covering N");
+    if (C_bf16 && !tma_store) {             // odd row stride: plain GEMM, then one conversion pass
+        if (int rc = gemm_bf16(A_bf16, lda, a_mn, B_bf16, ldb, b_mn, C, ldc, M, N, K, bias, alpha, act, stream)) return rc;
+        return eb_convert_bf16(C, M, N, ldc, C_bf16, ldcb, 0, stream);
+    }
     if (tma_store) { if (int rc = g_make_map_c(&mc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc)) return rc; }
     else mc = ma;
     const int n_out_tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
