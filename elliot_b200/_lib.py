@@ -80,6 +80,7 @@ SIGNATURES = {
                                  c_void, c_void, c_void]),
     "eb_neumf_sample": (c_int, [c_i32, c_i32, c_void, c_void, c_int, c_u64, c_i64, c_void, c_void, c_void, c_void]),
     "eb_neumf_pair_h1": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_int, c_int, c_int, c_void, c_i64, c_void]),
+    "eb_neumf_pair_h1_f32": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_int, c_int, c_int, c_void, c_i64, c_void]),
     "eb_neumf_pair_head": (c_int, [c_void, c_void, c_i64, c_int, c_int, c_int, c_int, c_void, c_i64, c_void, c_void, c_void, c_i64,
                                    c_void]),
     "eb_gather_rows_f32": (c_int, [c_void, c_i64, c_void, c_i64, c_int, c_void, c_i64, c_void]),

@@ -384,8 +384,11 @@ static int gemm_bf16(const void *A_bf16, int64_t lda, bool a_mn, const void *B_b
     const int k_blocks = (K + G_BK - 1) / G_BK;
     // split-K: few output tiles with a long K (dh2 = dlogits . W4: 20 tiles, K = 26 744) leave most SMs idle and each
     // busy CTA load-latency bound; split the K range over the idle SMs and add the partial tiles into a zeroed C
+    // (the partial tiles are ADDED with atomics / TMA reduce: the summation order, hence the last bits, vary from run to run;
+    // EB_GEMM_SPLITK=0 keeps every GEMM single-pass and bit-reproducible at the cost of idle SMs on these shapes)
+    static const bool splitk_off = [] { const char *e = getenv("EB_GEMM_SPLITK"); return e && e[0] == '0'; }();
     int splits = 1;
-    if (!bias && act == 0 && !C_bf16 && n_out_tiles * 2 <= sm_count() && k_blocks >= 16) {
+    if (!splitk_off && !bias && act == 0 && !C_bf16 && n_out_tiles * 2 <= sm_count() && k_blocks >= 16) {
         splits = sm_count() / n_out_tiles;
         if (splits > k_blocks / 8) splits = k_blocks / 8;           // at least 8 k-blocks per work item
         if (splits < 1) splits = 1;

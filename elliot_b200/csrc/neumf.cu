@@ -162,6 +162,18 @@ __global__ void __launch_bounds__(256) neumf_pair_h1_kernel(const float *Au, int
     }
 }
 
+// the same in fp32 (checking mode, ops.exact_gemm): H1 stays unrounded
+__global__ void __launch_bounds__(256) neumf_pair_h1_f32_kernel(const float *Au, int64_t ldau, const float *Ai, int64_t ldai, const float *b1,
+                                                                int n_ub, int n_items, int h1, float *out, int64_t ldo) {
+    const int64_t total = (int64_t)n_ub * n_items * h1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % h1);
+        const int64_t pair = e / h1;
+        const int it = (int)(pair % n_items), ub = (int)(pair / n_items);
+        out[pair * ldo + c] = fmaxf(Au[(int64_t)ub * ldau + c] + Ai[(int64_t)it * ldai + c] + b1[c], 0.f);
+    }
+}
+
 // prob[(ub, i)] = sigmoid(bp + w_mf . (U_mf[u0+ub] * I_mf[i]) + w_mlp . h3[pair])
 __global__ void __launch_bounds__(256) neumf_pair_head_kernel(const float *Umf, const float *Imf, int64_t ldt, int f, int u0, int n_ub,
                                                               int n_items, const float *h3, int64_t ldh, const float *wp,
@@ -256,6 +268,15 @@ extern "C" int eb_neumf_pair_h1(const float *Au, int64_t ldau, const float *Ai, 
     EB_ARG(Au && Ai && b1 && out_bf16 && n_ub >= 1 && n_items >= 1 && h1 % 8 == 0 && ldo % 8 == 0 && ldau % 4 == 0 && ldai % 4 == 0, "bad argument");
     neumf_pair_h1_kernel<<<ngrid((int64_t)n_ub * n_items * (h1 / 4)), 256, 0, (cudaStream_t)stream>>>(Au, ldau, Ai, ldai, b1, n_ub, n_items,
                                                                                                        h1, (__nv_bfloat16 *)out_bf16, ldo);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
+extern "C" int eb_neumf_pair_h1_f32(const float *Au, int64_t ldau, const float *Ai, int64_t ldai, const float *b1, int n_ub, int n_items,
+                                    int h1, float *out, int64_t ldo, void *stream) {
+    EB_ARG(Au && Ai && b1 && out && n_ub >= 1 && n_items >= 1 && h1 >= 1 && ldo >= h1, "bad argument");
+    neumf_pair_h1_f32_kernel<<<ngrid((int64_t)n_ub * n_items * h1), 256, 0, (cudaStream_t)stream>>>(Au, ldau, Ai, ldai, b1, n_ub, n_items, h1,
+                                                                                                     out, ldo);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }

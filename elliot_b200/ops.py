@@ -540,6 +540,9 @@ def neumf_sample(n_users, n_items, indptr, indices, m, seed):
 
 def neumf_pair_h1(Au, Ai, b1, n_ub, n_items, h1, out):
     _need_cuda(Au, Ai, b1, out)
+    if out.dtype == torch.float32:                        # exact_gemm checking mode: the first layer stays fp32
+        _call("eb_neumf_pair_h1_f32", Au, _ptr(Au), Au.stride(0), _ptr(Ai), Ai.stride(0), _ptr(b1), n_ub, n_items, h1, _ptr(out), out.stride(0))
+        return
     _call("eb_neumf_pair_h1", Au, _ptr(Au), Au.stride(0), _ptr(Ai), Ai.stride(0), _ptr(b1), n_ub, n_items, h1, _ptr(out), out.stride(0))
 
 

@@ -132,7 +132,7 @@ class NeuralMatrixFactorizationModel:
         if getattr(self, "_Ai_step", None) != self.step:
             self._Ai = ops.gemm_bf16_tn(ops.to_bf16(P["I_mlp"]), W1i, ni, 4 * f, f); self._Ai_step = self.step
         pairs = nb * ni
-        h1 = torch.empty((pairs, 4 * f), dtype=torch.bfloat16, device=self.device)
+        h1 = torch.empty((pairs, 4 * f), dtype=self.Wb["W2"].dtype, device=self.device)       # bf16 (fp32 in checking mode)
         ops.neumf_pair_h1(Au, self._Ai, P["b1"], nb, ni, 4 * f, h1)
         h2 = ops.gemm_bf16_tn(h1, self.Wb["W2"], pairs, 2 * f, 4 * f, bias=P["b2"], act=2)
         h3 = ops.gemm_bf16_tn(ops.to_bf16(h2), self.Wb["W3"], pairs, f, 2 * f, bias=P["b3"], act=2)

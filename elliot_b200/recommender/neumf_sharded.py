@@ -160,7 +160,7 @@ class ShardedNeuMFModel:
             self._items_step = self.step
         Au = ops.gemm_bf16_tn(ops.to_bf16(P["U_mlp"][u0:u1]), self.Wb["W1"][:, :f], nb, 4 * f, f)
         pairs = nb * ni
-        h1 = torch.empty((pairs, 4 * f), dtype=torch.bfloat16, device=self.device)
+        h1 = torch.empty((pairs, 4 * f), dtype=self.Wb["W2"].dtype, device=self.device)       # bf16 (fp32 in checking mode)
         ops.neumf_pair_h1(Au, self._Ai, P["b1"], nb, ni, 4 * f, h1)
         h2 = ops.gemm_bf16_tn(h1, self.Wb["W2"], pairs, 2 * f, 4 * f, bias=P["b2"], act=2)
         h3 = ops.gemm_bf16_tn(ops.to_bf16(h2), self.Wb["W3"], pairs, f, 2 * f, bias=P["b3"], act=2)

@@ -265,6 +265,9 @@ int eb_neumf_sample(int32_t n_users, int32_t n_items, const int64_t *indptr, con
                     int64_t total, int32_t *out_u, int32_t *out_i, float *out_label, void *stream);
 int eb_neumf_pair_h1(const float *Au, int64_t ldau, const float *Ai, int64_t ldai, const float *b1, int n_ub, int n_items,
                      int h1, void *out_bf16, int64_t ldo, void *stream);
+/* checking mode (ops.exact_gemm): the same first layer kept in fp32 */
+int eb_neumf_pair_h1_f32(const float *Au, int64_t ldau, const float *Ai, int64_t ldai, const float *b1, int n_ub, int n_items,
+                         int h1, float *out, int64_t ldo, void *stream);
 int eb_neumf_pair_head(const float *Umf, const float *Imf, int64_t ldt, int f, int u0, int n_ub, int n_items, const float *h3,
                        int64_t ldh, const float *wp, const float *bp, float *prob, int64_t ldpr, void *stream);
 

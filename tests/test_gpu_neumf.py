@@ -66,6 +66,33 @@ def test_get_recs_equals_pointwise_forward_and_masks():
         assert len(set(idx[r]) & set(want)) >= 5                          # near-ties may swap under bf16
 
 
+def test_get_recs_lists_are_exact_with_the_fp32_checking_gemm():
+    """get_recs / get_top_k (neural_matrix_factorization_model.py:119-148) with the dense layers in fp32: the masked top-7 lists
+    equal the fp64 restatement's item for item (probabilities to 1e-5) — the 5-of-7 overlap accepted above is bf16 rounding of
+    near-ties, not a wiring error."""
+    nu, ni, f = 70, 333, 8
+    with ops.exact_gemm():
+        m = NeuralMatrixFactorizationModel(nu, ni, f, 1e-3, 3, DEV)
+        for k in ("U_mf", "I_mf", "U_mlp", "I_mlp"):
+            m.P[k].mul_(5.0)
+        m._refresh()
+        P = _ref_params(m)
+        rs = np.random.RandomState(1)
+        rows = [np.sort(rs.choice(ni, size=rs.randint(1, 30), replace=False)).astype(np.int32) for _ in range(nu)]
+        indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+        mp = torch.from_numpy(indptr).to(DEV); mi = torch.from_numpy(np.concatenate(rows)).to(DEV)
+        idx, val = m.get_recs_topk(10, 40, 7, mp, mi)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for r, uu in enumerate(range(10, 40)):
+        _, _, p = tfm.neumf_forward_backward(P, np.full(ni, uu), np.arange(ni), np.zeros(ni))
+        p[rows[uu]] = -np.inf
+        want = np.argsort(-p, kind="stable")[:7]
+        gaps = np.abs(np.diff(np.sort(p[np.isfinite(p)])[::-1][:8]))
+        if gaps.min() > 1e-5:                                              # skip rows whose top-8 holds an fp32-level tie
+            assert list(idx[r]) == list(want), (r, idx[r], want)
+        assert np.abs(val[r] - p[idx[r]]).max() < 1e-5
+
+
 def test_sampler_distribution():
     nu, ni, m_neg = 50, 200, 3
     rs = np.random.RandomState(2)
