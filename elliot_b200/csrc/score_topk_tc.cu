@@ -62,31 +62,45 @@ struct TcParams {
     int debug_mode;              // profiling only: 1 = TMEM read + max only, 2 = no compaction (results invalid)
 };
 
-constexpr int TC_BUF = 64;        // append buffer per user row (top-KC kept + up to BUF-KC pending)
+constexpr int TC_BUF = 64;        // append-buffer slots per user row over all epilogue groups (top-KC kept + pending)
 constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 columns if fewer than 8 slots are free
 
 // KP = padded K (multiple of 16): KB full 64-wide blocks (one 128-byte swizzle atom each) + a tail of KT = 0, 16 or 32
 // columns in its own narrower-swizzle block.  (A 48-column tail is rounded up to a full block by the host.)  Padding K
 // to a multiple of 64 instead — as round 1 did — costs 2.0x the MMA work at d = 64 + 2 bias columns (128 vs 80) and
 // 1.33x at d = 128 + 2 (192 vs 144).
-template <int KP> struct TcCfg {
+// NG = number of epilogue warpgroups.  NG = 1: warps 2-5 scan every tile, 32 kept candidates in a 64-slot buffer per row.
+// NG = 2: warps 2-5 take the even tiles, warps 6-9 the odd ones (global tile counter), so every scheduler has TWO epilogue
+// warps to overlap the TMEM-load / max-tree latency of one with the other.  Each group keeps KC/2 = 16 candidates in a
+// 32-slot buffer per row: the 16th best of half the stream sits at the same level as the 32nd best of the whole stream, so
+// the insert rate per item is that of NG = 1 (round 2a's NG = 2 kept 32 per group and paid 1.85x the inserts), the shared
+// memory is the same 64 KB, and the re-rank reads the two lists side by side (16 + 16 lanes) with tau = max of the two.
+// Each group double-buffers its own accumulator (4 x BN TMEM columns, BN <= 128).
+template <int KP, int NG_> struct TcCfg {
     static constexpr int KB = KP / 64;                       // full 64-wide K blocks
     static constexpr int KT = KP % 64;                       // tail columns
     static_assert(KT == 0 || KT == 16 || KT == 32, "K tail must be 0, 16 or 32 columns");
-    // Epilogue warpgroups.  NG = 2 (tile-parity split, two candidate lists per row merged per user block) is
-    // implemented and exact, but measured no faster than NG = 1 on B200: each half-stream has a lower threshold
-    // (1.85x more inserts) and the smaller B tiles it forces cost more than the extra warps gain.
-    static constexpr int NG = 1;
-    static constexpr int BN = KP <= 128 ? 256 : (KP <= 208 ? 128 : 64);                   // items per tile (UMMA N)
+    static constexpr int NG = NG_;
+    static constexpr int NACC = 2 * NG;                      // TMEM accumulators
+    static constexpr int KCG = TC_KC / NG;                   // candidates kept per row and group
+    static constexpr int BUFG = TC_BUF / NG;                 // buffer slots per row and group
+    static constexpr int ROWB = BUFG * 4;                    // bytes per buffer row (keys; the ids follow in a second array)
+    static constexpr int BN = NG == 2 ? (KP <= 208 ? 128 : 64)
+                                      : (KP <= 128 ? 256 : (KP <= 208 ? 128 : 64));       // items per tile (UMMA N)
+    static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
+    static constexpr int TMEM_COLS = NACC * BN;              // 256 or 512: a power of two
     static constexpr int THREADS = 64 + 128 * NG;            // TMA warp + MMA warp + NG x 4 epilogue warps
     static constexpr int A_BYTES = TC_BM * KP * 2;
     static constexpr int B_BYTES = BN * KP * 2;
-    static constexpr int CAND_BYTES = NG * TC_BM * TC_BUF * 8;
-    static constexpr int FIXED = A_BYTES + CAND_BYTES + 1024 /*merged cnt/thresh*/ + 256;
+    static constexpr int CAND_BYTES = TC_BM * TC_BUF * 8;    // all groups together
+    static constexpr int MRG_BYTES = 2048;                   // per-row {cnt, thresh} of every group after the last tile
+    static constexpr int FIXED = A_BYTES + CAND_BYTES + MRG_BYTES + 256;
     static constexpr int ROOM = (232448 - FIXED) / B_BYTES;  // 227 KB of dynamic shared memory per CTA
     static constexpr int STAGES = ROOM >= 4 ? 4 : ROOM;
     static_assert(STAGES >= 2, "B ring needs two stages");
-    static constexpr int SMEM = FIXED + STAGES * B_BYTES;
+    static constexpr int USED = FIXED + STAGES * B_BYTES;
+    static constexpr int SMEM = 232448;                      // everything: what is left caches the user block's train-mask rows
+    static constexpr int MASKC = (SMEM - USED) / 4;          // cached mask entries (int32) per user block
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -99,6 +113,16 @@ __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// binary search for `key` in the sorted int32 row at shared-memory address `a` (the cached copy of a train-mask row)
+__device__ __forceinline__ bool contains_sorted_smem(uint32_t a, int len, int32_t key) {
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lds_s32(a + 4u * (uint32_t)mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo < len && lds_s32(a + 4u * (uint32_t)lo) == key;
+}
 
 constexpr uint32_t TC_KEY_NEG = 0x007FFFC0u;     // sortable key of -inf with the tie-break bits cleared
 
@@ -113,47 +137,61 @@ __device__ __forceinline__ float tc_upper_of(uint32_t key) {       // largest fl
     return __uint_as_float(b);
 }
 
-// Warp-cooperative compaction of ONE row of the candidate buffer (all 32 lanes call it together):
-// rank the row's 64 keys by counting (broadcast reads, no shuffles), keep ranks < KC in sorted order,
-// refill the rest with -inf.  Returns (number of valid kept entries, bits of the new threshold).
+// Warp-cooperative compaction of ONE row of the candidate buffer (all 32 lanes call it together): rank the row's BUFG keys
+// by counting (broadcast reads, no shuffles), keep ranks < KCG in sorted order, refill the rest with -inf.  BUFG = 64: two
+// keys per lane; BUFG = 32: one.  Returns (number of valid kept entries, bits of the new threshold).
 // Deliberately NOT inlined: it is called from every 8-column group of the unrolled scan and the
 // kernel must stay inside the instruction cache.
+template <int BUFG, int KCG>
 __device__ __noinline__ uint2 tc_compact_row(uint32_t bk, uint32_t bi, int rrow, int lane, int rl, const int32_t *mrow,
-                                             int n_items) {
-    const int p0 = (lane + rrow) & 63, p1 = (lane + 32 + rrow) & 63;
-    uint32_t k0 = (uint32_t)lds_s32(bk + 4u * p0), k1 = (uint32_t)lds_s32(bk + 4u * p1);
-    int i0 = lds_s32(bi + 4u * p0), i1 = lds_s32(bi + 4u * p1);
+                                             uint32_t mrow_smem, int n_items) {
+    constexpr int PM = BUFG - 1;
+    constexpr bool TWO = BUFG == 64;
+    const int p0 = (lane + rrow) & PM, p1 = (lane + 32 + rrow) & PM;
+    uint32_t k0 = (uint32_t)lds_s32(bk + 4u * p0), k1 = TWO ? (uint32_t)lds_s32(bk + 4u * p1) : 0u;
+    int i0 = lds_s32(bi + 4u * p0), i1 = TWO ? lds_s32(bi + 4u * p1) : 0;
     // train items (-inf in the reference) and the zero rows TMA pads past the catalogue
     bool d0 = false, d1 = false;
-    if (k0 > (TC_KEY_NEG | 63u)) d0 = i0 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i0));
-    if (k1 > (TC_KEY_NEG | 63u)) d1 = i1 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i1));
+    // (the row's mask entries are read from the block's shared-memory copy when they fit: the search is a chain of
+    // dependent loads, ~30 cycles each there against an L2 round trip each from global memory)
+    if (mrow_smem) {
+        if (k0 > (TC_KEY_NEG | 63u)) d0 = i0 >= n_items || (rl > 0 && contains_sorted_smem(mrow_smem, rl, i0));
+        if (TWO && k1 > (TC_KEY_NEG | 63u)) d1 = i1 >= n_items || (rl > 0 && contains_sorted_smem(mrow_smem, rl, i1));
+    } else {
+        if (k0 > (TC_KEY_NEG | 63u)) d0 = i0 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i0));
+        if (TWO && k1 > (TC_KEY_NEG | 63u)) d1 = i1 >= n_items || (rl > 0 && contains_sorted(mrow, rl, i1));
+    }
     if (d0) { k0 = TC_KEY_NEG | (uint32_t)(63 - p0); sts_s32(bk + 4u * p0, (int)k0); }
-    if (d1) { k1 = TC_KEY_NEG | (uint32_t)(63 - p1); sts_s32(bk + 4u * p1, (int)k1); }
+    if (TWO && d1) { k1 = TC_KEY_NEG | (uint32_t)(63 - p1); sts_s32(bk + 4u * p1, (int)k1); }
     __syncwarp();
     int r0 = 0, r1 = 0;
 #pragma unroll
-    for (int j = 0; j < 64; j += 4) {
+    for (int j = 0; j < BUFG; j += 4) {
         uint32_t x0, x1, x2, x3;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(bk + 4u * j));
         r0 += (x0 > k0) + (x1 > k0) + (x2 > k0) + (x3 > k0);
-        r1 += (x0 > k1) + (x1 > k1) + (x2 > k1) + (x3 > k1);
+        if (TWO) r1 += (x0 > k1) + (x1 > k1) + (x2 > k1) + (x3 > k1);
     }
     __syncwarp();                     // all reads done before the row is rewritten
-    const int n0 = (r0 + rrow) & 63, n1 = (r1 + rrow) & 63;
-    const bool keep0 = r0 < TC_KC && k0 > (TC_KEY_NEG | 63u), keep1 = r1 < TC_KC && k1 > (TC_KEY_NEG | 63u);
+    const int n0 = (r0 + rrow) & PM, n1 = (r1 + rrow) & PM;
+    const bool keep0 = r0 < KCG && k0 > (TC_KEY_NEG | 63u), keep1 = TWO && r1 < KCG && k1 > (TC_KEY_NEG | 63u);
+    // without the second key, ranks >= 32 never occur and every physical slot gets exactly one writer (its rank is unique)
     sts_s32(bk + 4u * n0, (int)(keep0 ? ((k0 & ~63u) | (uint32_t)(63 - n0)) : (TC_KEY_NEG | (uint32_t)(63 - n0))));
-    sts_s32(bk + 4u * n1, (int)(keep1 ? ((k1 & ~63u) | (uint32_t)(63 - n1)) : (TC_KEY_NEG | (uint32_t)(63 - n1))));
+    if (TWO) sts_s32(bk + 4u * n1, (int)(keep1 ? ((k1 & ~63u) | (uint32_t)(63 - n1)) : (TC_KEY_NEG | (uint32_t)(63 - n1))));
     if (keep0) sts_s32(bi + 4u * n0, i0);
     if (keep1) sts_s32(bi + 4u * n1, i1);
-    const int nvalid = __popc(__ballot_sync(0xffffffffu, keep0)) + __popc(__ballot_sync(0xffffffffu, keep1));
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, keep0)) + (TWO ? __popc(__ballot_sync(0xffffffffu, keep1)) : 0);
     __syncwarp();
-    const float th = nvalid == TC_KC ? tc_upper_of((uint32_t)lds_s32(bk + 4u * ((TC_KC - 1 + rrow) & 63))) : -CUDART_INF_F;
+    const float th = nvalid == KCG ? tc_upper_of((uint32_t)lds_s32(bk + 4u * ((KCG - 1 + rrow) & PM))) : -CUDART_INF_F;
     return make_uint2((uint32_t)nvalid, __float_as_uint(th));
 }
 
 // compaction of all rows of this warp selected by `todo`; returns the calling lane's new (cnt, thresh)
+template <int BUFG, int KCG>
 __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint32_t cidx, int quad, int lane, int mlen,
-                                              int64_t mbeg, const int32_t *mask_indices, int n_items, int cnt, float thresh) {
+                                              int64_t mbeg, const int32_t *mask_indices, int64_t seg_beg, int n_cached,
+                                              uint32_t mcache, int n_items, int cnt, float thresh) {
+    constexpr uint32_t ROWB = BUFG * 4;
     __syncwarp();
     while (todo) {
         const int r = __ffs(todo) - 1;
@@ -161,37 +199,42 @@ __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint
         const int rrow = quad * 32 + r;
         const int rl = __shfl_sync(0xffffffffu, mlen, r);
         const int64_t rb = __shfl_sync(0xffffffffu, mbeg, r);
-        const uint2 res = tc_compact_row(ckey + 256u * (uint32_t)rrow, cidx + 256u * (uint32_t)rrow, rrow, lane, rl,
-                                         mask_indices + rb, n_items);
+        const int64_t rel = rb - seg_beg;                       // the row's offset inside the block's cached segment
+        const uint32_t ms = (rl > 0 && rel + rl <= (int64_t)n_cached) ? mcache + 4u * (uint32_t)rel : 0u;
+        const uint2 res = tc_compact_row<BUFG, KCG>(ckey + ROWB * (uint32_t)rrow, cidx + ROWB * (uint32_t)rrow, rrow, lane, rl,
+                                                    mask_indices + rb, ms, n_items);
         if (lane == r) {
             cnt = (int)res.x;
-            if (res.x == TC_KC) thresh = __uint_as_float(res.y);
+            if (res.x == KCG) thresh = __uint_as_float(res.y);
         }
     }
     __syncwarp();
     return make_uint2((uint32_t)cnt, __float_as_uint(thresh));
 }
 
-template <int KP, bool HAS_BIAS>
-__global__ void __launch_bounds__(TcCfg<KP>::THREADS, 1)
+template <int KP, bool HAS_BIAS, int NGT>
+__global__ void __launch_bounds__(TcCfg<KP, NGT>::THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmBt, const TcParams p) {
-    using C = TcCfg<KP>;
-    constexpr int KB = C::KB, KT = C::KT, BN = C::BN, S = C::STAGES, NG = C::NG;
+    using C = TcCfg<KP, NGT>;
+    constexpr int KB = C::KB, KT = C::KT, BN = C::BN, S = C::STAGES, NG = C::NG, NACC = C::NACC;
+    constexpr int KCG = C::KCG, BUFG = C::BUFG;
+    constexpr uint32_t ROWB = C::ROWB, GRPB = TC_BM * BUFG * 8;           // bytes per buffer row / per group (keys + ids)
     const bool DUMP = p.dump != nullptr;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
     uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
     const uint32_t cval = smem_u32(sB + S * C::B_BYTES);                     // float [BUF][128]
-    const uint32_t mrg = cval + C::CAND_BYTES;                               // merged per-row {cnt[128], thresh[128]}
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + S * C::B_BYTES + C::CAND_BYTES + 1024);
+    const uint32_t mrg = cval + C::CAND_BYTES;                               // per group: {cnt[128], thresh[128]}
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + S * C::B_BYTES + C::CAND_BYTES + C::MRG_BYTES);
     const uint32_t bar0 = smem_u32(bars);
     auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(S + s); };
     const uint32_t A_FULL = bar0 + 8u * (2 * S), A_EMPTY = bar0 + 8u * (2 * S + 1);
     auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * S + 2 + a); };
-    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * S + 4 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 6);
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * S + 2 + NACC + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 + 2 * NACC);
+    const uint32_t mcache = smem_u32(sm + C::USED);                          // int32 [MASKC]: the user block's train-mask rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.n_items + BN - 1) / BN;
@@ -201,12 +244,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (smem_u32(sm) & 1023u) __trap();             // SWIZZLE_128B tiles need 1024-byte alignment
         for (int s = 0; s < S; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
-        for (int a = 0; a < 2; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        for (int a = 0; a < NACC; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         if (KT) { tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmBt); }
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -240,8 +283,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x, it++) {
                 mbar_wait(A_FULL, it & 1);
                 for (int t = 0; t < n_tiles; t++, tile++) {
-                    const int acc = tile & 1;
-                    mbar_wait(ACC_EMPTY(acc), ((tile >> 1) & 1) ^ 1);
+                    const int acc = tile % NACC;      // accumulator acc belongs to epilogue group acc % NG
+                    mbar_wait(ACC_EMPTY(acc), ((tile / NACC) & 1) ^ 1);
                     mbar_wait(B_FULL(s), ph);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -271,17 +314,16 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else {
         // ===================== epilogue: warps 2..5 (group 0) and, if NG == 2, warps 6..9 (group 1) =====================
-        // Group g owns TMEM accumulator g, i.e. the tiles with (global tile counter & 1) == g, and its own candidate
-        // buffers; the two per-row lists are merged at the end of every user block.
+        // Group g owns the tiles with (global tile counter % NG) == g, the TMEM accumulators g and g + NG, and its own
+        // candidate buffers; the re-rank at the end of every user block reads the groups' lists side by side.
         const int grp = NG == 2 ? ((warp - 2) >> 2) : 0;
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;             // row inside the 128-user block
         const float NEG = -CUDART_INF_F;
-        // candidate buffer: row-major [128 rows][64 slots] of sortable keys + item ids; logical slot s of row r
-        // lives at physical position (s + r) & 63 (rotation: conflict-free appends AND conflict-free row reads)
-        const uint32_t ckey = cval + (uint32_t)grp * (TC_BM * TC_BUF * 8);   // uint32 keys [128][64], then ids [128][64]
-        const uint32_t cidx = ckey + TC_BM * TC_BUF * 4;
-        const uint32_t ckey0 = cval, cidx0 = cval + TC_BM * TC_BUF * 4;       // group 0's buffers hold the merged lists
+        // candidate buffer: row-major [128 rows][BUFG slots] of sortable keys + item ids; logical slot s of row r
+        // lives at physical position (s + r) & (BUFG - 1) (rotation: conflict-free appends AND conflict-free row reads)
+        const uint32_t ckey = cval + (uint32_t)grp * GRPB;                    // uint32 keys [128][BUFG], then ids [128][BUFG]
+        const uint32_t cidx = ckey + TC_BM * BUFG * 4;
         uint32_t tile = 0;
         long long c_wait = 0, c_ld = 0, c_scan = 0, c_comp = 0, c_rank = 0, n_comp = 0, n_slow = 0, n_grp = 0;
         const bool prof = p.prof != nullptr && warp == 2;
@@ -292,24 +334,34 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int u = p.user_begin + (valid ? q : 0);
             int64_t mbeg = 0; int mlen = 0;
             if (valid && p.mask_indptr) { mbeg = p.mask_indptr[u]; mlen = (int)(p.mask_indptr[u + 1] - mbeg); }
+            // the CSR rows of the block's 128 consecutive users are ONE contiguous segment: copy as much of it as fits
+            int64_t seg_beg = 0; int n_cached = 0;
+            if (p.mask_indptr && C::MASKC > 0) {
+                const int q1 = min(mb * TC_BM + TC_BM, p.n_sel);
+                seg_beg = p.mask_indptr[p.user_begin + mb * TC_BM];
+                n_cached = (int)min(p.mask_indptr[p.user_begin + q1] - seg_beg, (int64_t)C::MASKC);
+                for (int e = (int)threadIdx.x - 64; e < n_cached; e += EPI_THREADS) sts_s32(mcache + 4u * (uint32_t)e, __ldg(p.mask_indices + seg_beg + e));
+            }
+            named_bar_sync(3, EPI_THREADS);
             int cnt = 0;                              // filled logical slots of my row
             float thresh = (valid && p.debug_mode != 1) ? NEG : CUDART_INF_F;   // upper bound of everything dropped so far
-            const uint32_t my_key = ckey + 256u * (uint32_t)row, my_idx = cidx + 256u * (uint32_t)row;
+            const uint32_t my_key = ckey + ROWB * (uint32_t)row, my_idx = cidx + ROWB * (uint32_t)row;
             // invariant: logical slots >= cnt hold -inf keys
 #pragma unroll 8
-            for (int sl = 0; sl < TC_BUF; sl++) sts_s32(my_key + 4u * (uint32_t)sl, (int)(TC_KEY_NEG | (uint32_t)(63 - sl)));
+            for (int sl = 0; sl < BUFG; sl++) sts_s32(my_key + 4u * (uint32_t)sl, (int)(TC_KEY_NEG | (uint32_t)(63 - sl)));
             __syncwarp();
 
             auto compact = [&](uint32_t todo) {
-                const uint2 res = tc_compact_rows(todo, ckey, cidx, quad, lane, mlen, mbeg, p.mask_indices, p.n_items, cnt, thresh);
+                const uint2 res = tc_compact_rows<BUFG, KCG>(todo, ckey, cidx, quad, lane, mlen, mbeg, p.mask_indices, seg_beg, n_cached,
+                                                             mcache, p.n_items, cnt, thresh);
                 cnt = (int)res.x; thresh = __uint_as_float(res.y);
             };
 
             for (int t = 0; t < n_tiles; t++, tile++) {
-                const int acc = tile & 1;
-                if (NG == 2 && acc != grp) continue;
+                const int acc = tile % NACC;
+                if (NG == 2 && (acc & 1) != grp) continue;
                 long long t0 = prof ? clock64() : 0;
-                mbar_wait(ACC_FULL(acc), (tile >> 1) & 1);
+                mbar_wait(ACC_FULL(acc), (tile / NACC) & 1);
                 tc_fence_after();
                 if (prof) c_wait += clock64() - t0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
@@ -346,8 +398,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const float bm = s8 < 4 ? bm0 : bm1;
                         if (!__any_sync(0xffffffffu, g[s8] + bm > thresh)) continue;
                         n_grp++;
-                        const uint32_t todo = __ballot_sync(0xffffffffu, cnt > TC_BUF - TC_SLACK);
-                        if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > TC_BUF - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
+                        const uint32_t todo = __ballot_sync(0xffffffffu, cnt > BUFG - TC_SLACK);
+                        if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > BUFG - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
                         // Append survivors one at a time, largest first: locate the group's max with static
                         // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
                         // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
@@ -363,7 +415,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int c = 6; c >= 0; c--) am = (w8[c] == gm) ? c : am;      // first position holding the max
                             const uint32_t take = gm > thresh ? 1u : 0u;
-                            const int pos = (cnt + row) & 63;
+                            const int pos = (cnt + row) & (BUFG - 1);
                             const uint32_t key = tc_key_of(gm, pos);
                             asm volatile(
                                 "{\n\t.reg .pred p;\n\t"
@@ -389,34 +441,10 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
             long long t4 = prof ? clock64() : 0;
             compact(__ballot_sync(0xffffffffu, valid));
-            if (NG == 2) {
-                // ---- merge the two groups' lists into group 0's buffer
-                if (grp == 1) sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);      // partner threshold, read by group 0
-                named_bar_sync(1, EPI_THREADS);
-                if (grp == 0) {
-                    const uint32_t pkey = cval + TC_BM * TC_BUF * 8, pidx = pkey + TC_BM * TC_BUF * 4;
-                    for (int r = 0; r < 32; r++) {
-                        const int rrow = quad * 32 + r;
-                        const uint32_t src = 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63);
-                        const int dpos = (32 + lane + rrow) & 63;
-                        const uint32_t dst = 256u * (uint32_t)rrow + 4u * (uint32_t)dpos;
-                        const uint32_t k = (uint32_t)lds_s32(pkey + src);
-                        sts_s32(ckey0 + dst, (int)((k & ~63u) | (uint32_t)(63 - dpos)));
-                        sts_s32(cidx0 + dst, lds_s32(pidx + src));
-                    }
-                    __syncwarp();
-                    const float tp = lds_f32(mrg + 512u + 4u * (uint32_t)row);
-                    compact(__ballot_sync(0xffffffffu, valid));
-                    thresh = fmaxf(thresh, tp);                 // everything either group ever dropped is <= thresh
-                    sts_s32(mrg + 4u * (uint32_t)row, cnt);
-                    sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);
-                }
-                named_bar_sync(2, EPI_THREADS);
-            } else {
-                sts_s32(mrg + 4u * (uint32_t)row, cnt);
-                sts_f32(mrg + 512u + 4u * (uint32_t)row, thresh);
-                __syncwarp();
-            }
+            sts_s32(mrg + 1024u * (uint32_t)grp + 4u * (uint32_t)row, cnt);
+            sts_f32(mrg + 1024u * (uint32_t)grp + 512u + 4u * (uint32_t)row, thresh);
+            if (NG == 2) named_bar_sync(1, EPI_THREADS);      // both groups' lists are final
+            else __syncwarp();
 
             const float vmax_n = p.vstat[0], bmax_a = p.vstat[1];
             const float my_unorm = valid ? p.unorm[q] : 0.f;
@@ -427,10 +455,16 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int rq = mb * TC_BM + rrow;
                 if (rq >= p.n_sel) break;                                 // warp-uniform
                 const int ru = p.user_begin + rq;
-                const int rcount = lds_s32(mrg + 4u * (uint32_t)rrow);
-                const float rthresh = lds_f32(mrg + 512u + 4u * (uint32_t)rrow);
-                const bool have = lane < rcount;
-                const int my_i = have ? lds_s32(cidx0 + 256u * (uint32_t)rrow + 4u * (uint32_t)((lane + rrow) & 63)) : 0x7fffffff;
+                // lanes [g * KCG, g * KCG + cnt_g) take group g's list; everything either group dropped is <= the larger tau
+                const int lg = NG == 2 ? lane / KCG : 0, ls = lane - lg * KCG;
+                const int c0 = lds_s32(mrg + 4u * (uint32_t)rrow), c1 = NG == 2 ? lds_s32(mrg + 1024u + 4u * (uint32_t)rrow) : 0;
+                const int rcount = c0 + c1;
+                float rthresh = lds_f32(mrg + 512u + 4u * (uint32_t)rrow);
+                if (NG == 2) rthresh = fmaxf(rthresh, lds_f32(mrg + 1024u + 512u + 4u * (uint32_t)rrow));
+                const bool have = ls < (lg ? c1 : c0);
+                const int my_i = have ? lds_s32(cval + (uint32_t)lg * GRPB + TC_BM * BUFG * 4 + ROWB * (uint32_t)rrow +
+                                                4u * (uint32_t)((ls + rrow) & (BUFG - 1)))
+                                      : 0x7fffffff;
                 float my_v = NEG;
                 if (have) {
                     const float *ur = p.U + (int64_t)ru * p.ld;
@@ -490,7 +524,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
             }
             __syncwarp();
-            if (NG == 2) named_bar_sync(3, EPI_THREADS);      // group 0's buffer is free for the next user block
+            named_bar_sync(2, EPI_THREADS);      // every list has been read: buffers and mask cache are free for the next user block
             if (prof) c_rank += clock64() - t4;
         }
         if (prof && lane == 0 && blockIdx.x == 0) {
@@ -500,7 +534,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- preparation kernels
@@ -547,6 +581,8 @@ __global__ void tc_bias_kernel(const float *bias, int32_t n_items, float *bmax_c
 }
 
 // ---------------------------------------------------------------- host side
+extern "C" size_t eb_score_recheck_workspace_bytes(int64_t n_sel_max, int32_t n_items);    // score_topk.cu
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -601,7 +637,7 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
     L.bmax = off; off += al(((size_t)n_items + 31) / 32 * 4);
     L.flag_count = off; off += al(256);
     L.flag_list = off; off += al((size_t)n_sel * 4);
-    L.exact_bytes = (size_t)eb_score_topk_workspace_bytes(n_sel < 4096 ? n_sel : 4096, n_items, 4);
+    L.exact_bytes = eb_score_recheck_workspace_bytes(n_sel, n_items);
     L.exact_ws = off; off += al(L.exact_bytes);
     L.total = off;
     return L;
@@ -609,20 +645,20 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
 
 struct TcMaps { CUtensorMap a, b, at, bt; };
 
-template <int KP, bool HAS_BIAS>
+template <int KP, bool HAS_BIAS, int NG>
 static int launch_tc3(const TcMaps &m, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    auto kern = score_topk_tc_kernel<KP, HAS_BIAS>;
-    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP>::SMEM));
+    auto kern = score_topk_tc_kernel<KP, HAS_BIAS, NG>;
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP, NG>::SMEM));
     int grid = sm_count();
     if (grid > n_mblocks) grid = n_mblocks;
-    kern<<<grid, TcCfg<KP>::THREADS, TcCfg<KP>::SMEM, st>>>(m.a, m.b, m.at, m.bt, p);
+    kern<<<grid, TcCfg<KP, NG>::THREADS, TcCfg<KP, NG>::SMEM, st>>>(m.a, m.b, m.at, m.bt, p);
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
 
-template <int KP>
+template <int KP, int NG>
 static int launch_tc(void *ubf, void *vbf, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    using C = TcCfg<KP>;
+    using C = TcCfg<KP, NG>;
     TcMaps m;
     // a tile without full blocks (KP = 16 / 32) still needs valid descriptors in the unused slots
     const uint32_t bc = C::KB ? 64 : C::KT, tc = C::KT ? C::KT : 64;
@@ -631,7 +667,7 @@ static int launch_tc(void *ubf, void *vbf, const TcParams &p, int n_mblocks, cud
     if (int rc = make_map(&m.at, ubf, (uint64_t)p.n_sel, KP, tc, TC_BM)) return rc;
     if (int rc = make_map(&m.bt, vbf, (uint64_t)p.n_items, KP, tc, C::BN)) return rc;
     const bool hb = p.bias != nullptr && !p.bias_folded;    // epilogue adds the bias only when it is not folded into the MMA
-    return hb ? launch_tc3<KP, true>(m, p, n_mblocks, st) : launch_tc3<KP, false>(m, p, n_mblocks, st);
+    return hb ? launch_tc3<KP, true, NG>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG>(m, p, n_mblocks, st);
 }
 
 }  // namespace eb
@@ -695,9 +731,12 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     { const char *dbg = getenv("EB_TC_DEBUG"); p.debug_mode = dbg ? atoi(dbg) : 0; }
     p.prof = (stats_host && getenv("EB_TC_PROF")) ? (long long *)(flag_count + 16) : nullptr;
     const int n_mblocks = (int)((n_sel + TC_BM - 1) / TC_BM);
+    // epilogue warpgroups: two by default (see TcCfg); EB_TC_NG=1 selects the single-group kernel for A/B measurements
+    int ng = 2;
+    { const char *e = getenv("EB_TC_NG"); if (e && atoi(e) == 1) ng = 1; }
     int rc;
     switch (L.KP) {
-#define EB_TC_CASE(K) case K: rc = launch_tc<K>(ubf, vbf, p, n_mblocks, st); break;
+#define EB_TC_CASE(K) case K: rc = ng == 2 ? launch_tc<K, 2>(ubf, vbf, p, n_mblocks, st) : launch_tc<K, 1>(ubf, vbf, p, n_mblocks, st); break;
         EB_TC_CASE(16) EB_TC_CASE(32) EB_TC_CASE(64) EB_TC_CASE(80) EB_TC_CASE(96) EB_TC_CASE(128) EB_TC_CASE(144)
         EB_TC_CASE(160) EB_TC_CASE(192) EB_TC_CASE(208) EB_TC_CASE(224) EB_TC_CASE(256)
 #undef EB_TC_CASE

@@ -11,6 +11,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["2", "1"], ids=["two_epilogue_groups", "one_epilogue_group"])
+def _epilogue_groups(request, monkeypatch):
+    """every test runs against both kernels: two epilogue warpgroups (the default) and the single-group one (EB_TC_NG=1)"""
+    monkeypatch.setenv("EB_TC_NG", request.param)
+
+
 def _tables(nu, ni, d, seed, scale=0.1, bias=True):
     g = torch.Generator(device=DEV); g.manual_seed(seed)
     ld = ops.padded_dim(d)
@@ -72,6 +78,24 @@ def test_tc_adversarial_near_ties_fall_back_to_exact():
     i1, v1, st = ops.score_topk_tc(U, V, None, d, k)
     assert st["rechecked"] > 0
     assert torch.equal(i0, i1) and torch.equal(v0, v1)
+
+
+@pytest.mark.parametrize("nu,ndup,why", [(6000, 200, "more flagged users than the re-check filter's row capacity"),
+                                         (140, 1500, "more near-ties above the bound than one re-check list holds")])
+def test_tc_recheck_overflow_paths_stay_exact(nu, ndup, why):
+    """The re-check spreads the items over the grid and keeps short per-user lists; users it cannot hold (too many flagged
+    users, too many items above the bound) must still come out exact through the row-per-CTA kernel."""
+    ni, d, k = 4000, 64, 10
+    U, V, b = _tables(nu, ni, d, seed=13)
+    g = torch.Generator(device=DEV); g.manual_seed(6)
+    V[1:ndup + 1, :d] = V[0, :d] * (1 + 1e-4 * torch.randn(ndup, d, device=DEV, generator=g))
+    V[:ndup + 1] *= 4.0
+    b[:ndup + 1] = 0.0
+    mp, mi = _mask(nu, ni, 20, seed=3)
+    i0, v0 = ops.score_topk(U, V, b, d, k, mp, mi)
+    i1, v1, st = ops.score_topk_tc(U, V, b, d, k, mp, mi)
+    assert st["rechecked"] > (1024 if ndup == 200 else 10), (why, st)
+    assert torch.equal(i0, i1) and torch.equal(v0, v1), why
 
 
 def test_tc_heavy_mask_and_short_lists():

@@ -20,10 +20,29 @@ def run(nu, ni, d, k, per_user, label):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     kp = st["kp"]; fl = 2.0 * kp * ni * nu
-    print(f"{label}: {nu} users x {ni} items d={d} kp={kp}: {ms:.2f} ms  {nu/ms*1e3/1e6:.3f} M users/s  {fl/ms/1e9:.1f} TFLOP/s (padded K)  {2.0*d*ni*nu/ms/1e9:.1f} TFLOP/s (algorithmic)  rechecked {st['rechecked']}")
+    print(f"{label}: {nu} users x {ni} items d={d} kp={kp}: {ms:.2f} ms  {nu/ms*1e3/1e6:.3f} M users/s  {fl/ms/1e9:.1f} TFLOP/s (padded K)  {2.0*d*ni*nu/ms/1e9:.1f} TFLOP/s (algorithmic)  rechecked {st['rechecked']}  prof {st.get('prof')}")
     # spot-check vs exact kernel on 512 users
     i0, v0 = ops.score_topk(U, V, b, d, k, indptr, indices, user_begin=0, n_sel=512)
     print("   identical to exact kernel on 512 users:", torch.equal(i0, i1[:512]), torch.equal(v0, v1[:512]))
+if len(sys.argv) > 1 and sys.argv[1] == "ab":
+    # A/B of the epilogue layouts; EB_TC_DEBUG=3 certifies everything (no re-check) so the main kernel is timed alone;
+    # EB_TC_PROF=1 adds warp 2's cycle counters (accumulator wait, TMEM load, scan, compaction, re-rank; counts)
+    os.environ["EB_TC_PROF"] = "1"
+    for ng in ("1", "2"):
+        for dbg in ("0", "3"):
+            os.environ["EB_TC_NG"] = ng; os.environ["EB_TC_DEBUG"] = dbg
+            run(148 * 128 * 2, 100_000, 64, 10, 100, f"C2 ng={ng} dbg={dbg}")
+            run(148 * 128 * 2, 2_000_000, 128, 10, 100, f"C5 ng={ng} dbg={dbg}")
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "feed":
+    # EB_TC_DEBUG=1: the epilogue only reads TMEM and takes the max (no inserts): the TMA/MMA pipeline's own pace
+    os.environ["EB_TC_PROF"] = "1"
+    for ng in ("1", "2"):
+        for dbg in ("1", "2"):
+            os.environ["EB_TC_NG"] = ng; os.environ["EB_TC_DEBUG"] = dbg
+            run(148 * 128 * 2, 100_000, 64, 10, 100, f"C2 ng={ng} dbg={dbg}")
+            run(148 * 128 * 2, 2_000_000, 128, 10, 100, f"C5 ng={ng} dbg={dbg}")
+    sys.exit(0)
 run(148 * 128 * 4, 100_000, 64, 10, 100, "C2-shape")
 run(148 * 128 * 2, 2_000_000, 128, 10, 100, "C5-shape(per-GPU slice)")
 run(6040, 3706, 64, 10, 130, "C1-shape")
