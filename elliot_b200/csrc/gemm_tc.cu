@@ -59,7 +59,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto ACC_FULL = [&](int a) { return bar0 + 8u * (uint32_t)(2 * G_STAGES + a); };
     auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (uint32_t)(2 * G_STAGES + 2 + a); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * G_STAGES + 4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see elect_one_sync)
+    const int lane = threadIdx.x & 31;
     const int tiles_m = (p.M + G_BM - 1) / G_BM, tiles_n = (p.N + G_BN - 1) / G_BN;
     const int k_blocks_all = (p.K + G_BK - 1) / G_BK;
     const int kb_per = (k_blocks_all + p.splits - 1) / p.splits;     // k-blocks per split (the last may be shorter)
@@ -83,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0; uint32_t ph = 0;
             for (int work = blockIdx.x; work < n_tiles; work += gridDim.x) {
                 const int tile = work / p.splits, split = work % p.splits;
@@ -110,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // instruction descriptor: fp32 accum, bf16 A/B, K-major both, N=128, M=128
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24) |
                                        (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);      // a_major / b_major: 1 = MN-major
@@ -170,7 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int col0 = tn * G_BN + c0;
                     if (!empty && col0 < p.N && tm * G_BM + quad * 32 < p.M) {         // warp-uniform
                         const uint32_t box = smem_u32(epi + (quad * 2 + (chunk & 1)) * G_EPI_BOX);
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box used 2 chunks ago is read
+                        // the box used 2 chunks ago has been read (every lane asks: only the one that issued the stores has groups)
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         __syncwarp();
                         const int my_row = tm * G_BM + quad * 32 + lane;
 #pragma unroll
@@ -204,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA unit
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one_sync()) {
                             const int rr = tm * G_BM + quad * 32;
                             if (p.splits > 1)
                                 asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -259,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
         }
-        if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all boxes written before the CTA retires
+        if (p.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all boxes written before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -47,6 +47,7 @@ struct TcParams {
     int32_t n_sel;
     int k;
     // prepared by tc_prep kernels
+    const __nv_bfloat16 *ubf;    // bf16 user rows [n_sel][KP] (the A operand), read directly by the A-in-TMEM kernels
     const float *unorm;          // ||u|| per selected user
     const float *vstat;          // [0] = max ||v||, [1] = max |bias|
     const float *bmax_chunk;     // max bias per 32-item chunk (null if no bias)
@@ -76,27 +77,46 @@ constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 colu
 // the insert rate per item is that of NG = 1 (round 2a's NG = 2 kept 32 per group and paid 1.85x the inserts), the shared
 // memory is the same 64 KB, and the re-rank reads the two lists side by side (16 + 16 lanes) with tau = max of the two.
 // Each group double-buffers its own accumulator (4 x BN TMEM columns, BN <= 128).
-template <int KP, int NG_> struct TcCfg {
+// PAIR: two CTAs of a cluster (two SMs of one TPC) score 256 users against each item tile with ONE tcgen05.mma.cta_group::2
+// per K step: each CTA keeps its own 128 users (A tile, accumulators, candidate lists, epilogue warps) and loads only HALF of
+// the item tile's rows; the tensor cores of both SMs read the two halves from the two shared memories.  The item table then
+// crosses the L2 -> SM fabric once per 256 users instead of once per 128 — the feed that bounds the single-CTA kernel at
+// large catalogues (9.5 TB/s at 2 M x 144 bf16 with nothing but the MMA running).
+// ATM: the user block (the operand that stays for the whole item stream) lives in TMEM instead of shared memory: the epilogue
+// warps of group 0 write their rows there once per user block (tcgen05.st) and every MMA takes A from TMEM.  A K = 16 step of
+// an M = 128 x N = 128 MMA reads 4 KB of A and 4 KB of B from shared memory in its 64 cycles — all of the SM's 128 B/cycle,
+// before the TMA fill of the next tile and the epilogue's candidate buffers: measured ~100 cycles per step.  Without A it is
+// half.  TMEM: 128 columns for A (KP / 2 used) + 3 accumulators x 128 (tile t -> accumulator t % 3, group t % 2).
+template <int KP, int NG_, bool PAIR_ = false, bool ATM_ = false> struct TcCfg {
     static constexpr int KB = KP / 64;                       // full 64-wide K blocks
     static constexpr int KT = KP % 64;                       // tail columns
     static_assert(KT == 0 || KT == 16 || KT == 32, "K tail must be 0, 16 or 32 columns");
     static constexpr int NG = NG_;
-    static constexpr int NACC = 2 * NG;                      // TMEM accumulators
+    static constexpr bool PAIR = PAIR_;
+    // TMEM accumulators: two per epilogue group; PAIR widens the tile to 256 items (one M = 256 x N = 256 instruction per K
+    // step: per SM and MMA cycle the shared memory then serves half the operand bytes of two M = 128 x N = 128 ones) and
+    // keeps one accumulator per group — the groups alternate, so the MMA of one tile still overlaps the scan of the other
+    static constexpr bool ATM = ATM_;
+    static_assert(!(ATM && (PAIR || NG != 2)), "A-in-TMEM is built for the two-group single-CTA kernel");
+    static constexpr int NACC = ATM ? 3 : (PAIR ? NG : 2 * NG);
+    static constexpr int ACC0 = ATM ? 128 : 0;               // first accumulator column
     static constexpr int KCG = TC_KC / NG;                   // candidates kept per row and group
     static constexpr int BUFG = TC_BUF / NG;                 // buffer slots per row and group
     static constexpr int ROWB = BUFG * 4;                    // bytes per buffer row (keys; the ids follow in a second array)
-    static constexpr int BN = NG == 2 ? (KP <= 208 ? 128 : 64)
-                                      : (KP <= 128 ? 256 : (KP <= 208 ? 128 : 64));       // items per tile (UMMA N)
-    static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
-    static constexpr int TMEM_COLS = NACC * BN;              // 256 or 512: a power of two
+    static constexpr int BN = PAIR ? (KP <= 208 ? 256 : 128)
+                                   : (NG == 2 ? (KP <= 208 ? 128 : 64)
+                                              : (KP <= 128 ? 256 : (KP <= 208 ? 128 : 64)));   // items per tile (UMMA N)
+    static_assert(ACC0 + NACC * BN <= 512, "accumulators exceed TMEM");
+    static constexpr int TMEM_COLS = ATM ? 512 : NACC * BN;  // 256 or 512: a power of two
     static constexpr int THREADS = 64 + 128 * NG;            // TMA warp + MMA warp + NG x 4 epilogue warps
-    static constexpr int A_BYTES = TC_BM * KP * 2;
-    static constexpr int B_BYTES = BN * KP * 2;
+    static constexpr int A_BYTES = ATM ? 0 : TC_BM * KP * 2;
+    static constexpr int BNL = PAIR ? BN / 2 : BN;           // item rows of a tile THIS CTA loads
+    static constexpr int B_BYTES = BNL * KP * 2;
     static constexpr int CAND_BYTES = TC_BM * TC_BUF * 8;    // all groups together
     static constexpr int MRG_BYTES = 2048;                   // per-row {cnt, thresh} of every group after the last tile
     static constexpr int FIXED = A_BYTES + CAND_BYTES + MRG_BYTES + 256;
     static constexpr int ROOM = (232448 - FIXED) / B_BYTES;  // 227 KB of dynamic shared memory per CTA
-    static constexpr int STAGES = ROOM >= 4 ? 4 : ROOM;
+    static constexpr int STAGES = ROOM >= (PAIR ? 6 : 4) ? (PAIR ? 6 : 4) : ROOM;
     static_assert(STAGES >= 2, "B ring needs two stages");
     static constexpr int USED = FIXED + STAGES * B_BYTES;
     static constexpr int SMEM = 232448;                      // everything: what is left caches the user block's train-mask rows
@@ -212,12 +232,12 @@ __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint
     return make_uint2((uint32_t)cnt, __float_as_uint(thresh));
 }
 
-template <int KP, bool HAS_BIAS, int NGT>
-__global__ void __launch_bounds__(TcCfg<KP, NGT>::THREADS, 1)
+template <int KP, bool HAS_BIAS, int NGT, bool PAIR, bool ATM>
+__global__ void __launch_bounds__(TcCfg<KP, NGT, PAIR, ATM>::THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmBt, const TcParams p) {
-    using C = TcCfg<KP, NGT>;
-    constexpr int KB = C::KB, KT = C::KT, BN = C::BN, S = C::STAGES, NG = C::NG, NACC = C::NACC;
+    using C = TcCfg<KP, NGT, PAIR, ATM>;
+    constexpr int KB = C::KB, KT = C::KT, BN = C::BN, BNL = C::BNL, S = C::STAGES, NG = C::NG, NACC = C::NACC;
     constexpr int KCG = C::KCG, BUFG = C::BUFG;
     constexpr uint32_t ROWB = C::ROWB, GRPB = TC_BM * BUFG * 8;           // bytes per buffer row / per group (keys + ids)
     const bool DUMP = p.dump != nullptr;
@@ -236,81 +256,130 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 + 2 * NACC);
     const uint32_t mcache = smem_u32(sm + C::USED);                          // int32 [MASKC]: the user block's train-mask rows
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role branches do not diverge
+    const int lane = threadIdx.x & 31;
     const int n_tiles = (p.n_items + BN - 1) / BN;
     const int n_mblocks = (p.n_sel + TC_BM - 1) / TC_BM;
-
+    // work units: user blocks, or (PAIR) pairs of user blocks — CTA rank r of the cluster takes block 2 * unit + r; with an
+    // odd number of blocks the last unit's second CTA runs a phantom block (TMA zero-fills its A tile, every row invalid)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int n_units = PAIR ? (n_mblocks + 1) / 2 : n_mblocks;
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // PAIR: the operand barriers the MMA thread waits on (A_FULL, B_FULL) and the ones it is released by (ACC_EMPTY) live
+    // in the LEADER (rank 0); the ones it releases (A_EMPTY, B_EMPTY, ACC_FULL) exist in both CTAs (multicast commit)
     if (threadIdx.x == 0) {
         if (smem_u32(sm) & 1023u) __trap();             // SWIZZLE_128B tiles need 1024-byte alignment
-        for (int s = 0; s < S; s++) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
-        mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
-        for (int a = 0; a < NACC; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        for (int s = 0; s < S; s++) { mbar_init(B_FULL(s), PAIR ? 2 : 1); mbar_init(B_EMPTY(s), 1); }
+        mbar_init(A_FULL, ATM ? 4 : (PAIR ? 2 : 1)); mbar_init(A_EMPTY, 1);
+        for (int a = 0; a < NACC; a++) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), PAIR ? 8 : 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
         if (KT) { tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmBt); }
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), C::TMEM_COLS); else tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0; uint32_t ph = 0; uint32_t it = 0;
-            for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x, it++) {
-                mbar_wait(A_EMPTY, (it & 1) ^ 1);
-                mbar_expect_tx(A_FULL, C::A_BYTES);
-                for (int kb = 0; kb < KB; kb++)
-                    tma_load_2d(smem_u32(sA + kb * (TC_BM * 128)), &tmA, A_FULL, kb * 64, mb * TC_BM);
-                if (KT) tma_load_2d(smem_u32(sA + KB * (TC_BM * 128)), &tmAt, A_FULL, KB * 64, mb * TC_BM);
+            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            long long w_bempty = 0;
+            const uint32_t a_full = PAIR ? mapa_cluster(A_FULL, 0) : A_FULL;
+            for (int un = unit0; un < n_units; un += unit_step, it++) {
+                const int mb = PAIR ? 2 * un + (int)rank : un;
+                if (!ATM) mbar_wait(A_EMPTY, (it & 1) ^ 1);
+                if (ATM) {}                                   // the user block goes to TMEM through the epilogue warps
+                else if (!PAIR) mbar_expect_tx(A_FULL, C::A_BYTES);
+                else if (rank == 0) mbar_expect_tx(A_FULL, 2 * C::A_BYTES);     // both CTAs' A tiles are credited to the leader
+                else mbar_arrive_cluster(a_full);
+                for (int kb = 0; kb < KB && !ATM; kb++) {
+                    if (PAIR) tma_load_2d_pair(smem_u32(sA + kb * (TC_BM * 128)), &tmA, a_full, kb * 64, mb * TC_BM);
+                    else tma_load_2d(smem_u32(sA + kb * (TC_BM * 128)), &tmA, A_FULL, kb * 64, mb * TC_BM);
+                }
+                if (KT && !ATM) {
+                    if (PAIR) tma_load_2d_pair(smem_u32(sA + KB * (TC_BM * 128)), &tmAt, a_full, KB * 64, mb * TC_BM);
+                    else tma_load_2d(smem_u32(sA + KB * (TC_BM * 128)), &tmAt, A_FULL, KB * 64, mb * TC_BM);
+                }
                 for (int t = 0; t < n_tiles; t++) {
+                    const long long t0 = prof ? clock64() : 0;
                     mbar_wait(B_EMPTY(s), ph ^ 1);
-                    mbar_expect_tx(B_FULL(s), C::B_BYTES);
-                    for (int kb = 0; kb < KB; kb++)
-                        tma_load_2d(smem_u32(sB + s * C::B_BYTES + kb * (BN * 128)), &tmB, B_FULL(s), kb * 64, t * BN);
-                    if (KT) tma_load_2d(smem_u32(sB + s * C::B_BYTES + KB * (BN * 128)), &tmBt, B_FULL(s), KB * 64, t * BN);
+                    if (prof) w_bempty += clock64() - t0;
+                    const uint32_t b_full = PAIR ? mapa_cluster(B_FULL(s), 0) : B_FULL(s);
+                    if (!PAIR) mbar_expect_tx(B_FULL(s), C::B_BYTES);
+                    else if (rank == 0) mbar_expect_tx(B_FULL(s), 2 * C::B_BYTES);
+                    else mbar_arrive_cluster(b_full);
+                    const int row0 = t * BN + (int)rank * BNL;                  // PAIR: this CTA's half of the tile's item rows
+                    for (int kb = 0; kb < KB; kb++) {
+                        if (PAIR) tma_load_2d_pair(smem_u32(sB + s * C::B_BYTES + kb * (BNL * 128)), &tmB, b_full, kb * 64, row0);
+                        else tma_load_2d(smem_u32(sB + s * C::B_BYTES + kb * (BNL * 128)), &tmB, B_FULL(s), kb * 64, row0);
+                    }
+                    if (KT) {
+                        if (PAIR) tma_load_2d_pair(smem_u32(sB + s * C::B_BYTES + KB * (BNL * 128)), &tmBt, b_full, KB * 64, row0);
+                        else tma_load_2d(smem_u32(sB + s * C::B_BYTES + KB * (BNL * 128)), &tmBt, B_FULL(s), KB * 64, row0);
+                    }
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
+            }
+            if (prof) p.prof[12] = w_bempty;
+            if (PAIR) {
+                // drain: the leader's last multicast commits must have landed in this CTA's barriers before it may exit
+                for (int i = 0; i < S; i++) { mbar_wait(B_EMPTY(s), ph ^ 1); if (++s == S) { s = 0; ph ^= 1; } }
+                mbar_wait(A_EMPTY, (it & 1) ^ 1);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+        // ===================== MMA issuer (PAIR: the leader CTA's, for both) =====================
+        if (rank == 0 && elect_one_sync()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, bool accumulate) {
+                if (PAIR) umma_bf16_pair(d, da, db, idesc, accumulate); else umma_bf16(d, da, db, idesc, accumulate);
+            };
+            auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int s = 0; uint32_t ph = 0; uint32_t it = 0; uint32_t tile = 0;
-            for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x, it++) {
-                mbar_wait(A_FULL, it & 1);
+            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            long long w_acc = 0, w_bfull = 0, w_afull = 0, t_all = prof ? clock64() : 0;
+            for (int un = unit0; un < n_units; un += unit_step, it++) {
+                { const long long t0 = prof ? clock64() : 0; mbar_wait(A_FULL, it & 1); if (prof) w_afull += clock64() - t0; }
                 for (int t = 0; t < n_tiles; t++, tile++) {
                     const int acc = tile % NACC;      // accumulator acc belongs to epilogue group acc % NG
+                    const long long t0 = prof ? clock64() : 0;
                     mbar_wait(ACC_EMPTY(acc), ((tile / NACC) & 1) ^ 1);
+                    const long long t1 = prof ? clock64() : 0;
                     mbar_wait(B_FULL(s), ph);
+                    if (prof) { w_acc += t1 - t0; w_bfull += clock64() - t1; }
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(C::ACC0 + acc * BN);
 #pragma unroll
                     for (int kb = 0; kb < KB; kb++) {
                         const uint32_t a_addr = smem_u32(sA + kb * (TC_BM * 128));
-                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + kb * (BN * 128));
+                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + kb * (BNL * 128));
 #pragma unroll
-                        for (int k = 0; k < 4; k++)   // UMMA_K = 16 bf16 = 32 B inside the 128-B swizzle atom
-                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                      (kb | k) != 0);
+                        for (int k = 0; k < 4; k++) { // UMMA_K = 16 bf16 = 32 B inside the 128-B swizzle atom = 8 TMEM columns of A
+                            if (ATM) umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((kb * 4 + k) * 8), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                            else mma(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), (kb | k) != 0);
+                        }
                     }
                     if (KT) {                         // K tail: one (16 columns) or two (32) more K = 16 steps
                         const uint32_t a_addr = smem_u32(sA + KB * (TC_BM * 128));
-                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + KB * (BN * 128));
+                        const uint32_t b_addr = smem_u32(sB + s * C::B_BYTES + KB * (BNL * 128));
 #pragma unroll
-                        for (int k = 0; k < KT / 16; k++)
-                            umma_bf16(d_tmem, umma_desc_tail<KT ? KT : 16>(a_addr + k * 32), umma_desc_tail<KT ? KT : 16>(b_addr + k * 32),
-                                      idesc, (KB | k) != 0);
+                        for (int k = 0; k < KT / 16; k++) {
+                            if (ATM) umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((KB * 4 + k) * 8), umma_desc_tail<KT ? KT : 16>(b_addr + k * 32), idesc, (KB | k) != 0);
+                            else mma(d_tmem, umma_desc_tail<KT ? KT : 16>(a_addr + k * 32), umma_desc_tail<KT ? KT : 16>(b_addr + k * 32),
+                                     (KB | k) != 0);
+                        }
                     }
-                    umma_commit(B_EMPTY(s));          // B stage reusable once these MMAs retire
-                    umma_commit(ACC_FULL(acc));       // accumulator ready for the epilogue
+                    commit(B_EMPTY(s));               // B stage reusable once these MMAs retire
+                    commit(ACC_FULL(acc));            // accumulator ready for the epilogue
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(A_EMPTY);                 // A reusable after the block's last MMA
+                commit(A_EMPTY);                      // A reusable after the block's last MMA
             }
+            if (prof) { p.prof[8] = w_acc; p.prof[9] = w_bfull; p.prof[10] = w_afull; p.prof[11] = clock64() - t_all; }
         }
     } else {
         // ===================== epilogue: warps 2..5 (group 0) and, if NG == 2, warps 6..9 (group 1) =====================
@@ -328,7 +397,9 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         long long c_wait = 0, c_ld = 0, c_scan = 0, c_comp = 0, c_rank = 0, n_comp = 0, n_slow = 0, n_grp = 0;
         const bool prof = p.prof != nullptr && warp == 2;
         constexpr int EPI_THREADS = 128 * NG;
-        for (int mb = blockIdx.x; mb < n_mblocks; mb += gridDim.x) {
+        uint32_t ublk = 0;                            // user blocks this CTA has started
+        for (int un = unit0; un < n_units; un += unit_step, ublk++) {
+            const int mb = PAIR ? 2 * un + (int)rank : un;
             const int q = mb * TC_BM + row;           // position in the selected user range
             const bool valid = q < p.n_sel;
             const int u = p.user_begin + (valid ? q : 0);
@@ -336,13 +407,30 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (valid && p.mask_indptr) { mbeg = p.mask_indptr[u]; mlen = (int)(p.mask_indptr[u + 1] - mbeg); }
             // the CSR rows of the block's 128 consecutive users are ONE contiguous segment: copy as much of it as fits
             int64_t seg_beg = 0; int n_cached = 0;
-            if (p.mask_indptr && C::MASKC > 0) {
+            if (p.mask_indptr && C::MASKC > 0 && mb < n_mblocks) {
                 const int q1 = min(mb * TC_BM + TC_BM, p.n_sel);
                 seg_beg = p.mask_indptr[p.user_begin + mb * TC_BM];
                 n_cached = (int)min(p.mask_indptr[p.user_begin + q1] - seg_beg, (int64_t)C::MASKC);
                 for (int e = (int)threadIdx.x - 64; e < n_cached; e += EPI_THREADS) sts_s32(mcache + 4u * (uint32_t)e, __ldg(p.mask_indices + seg_beg + e));
             }
             named_bar_sync(3, EPI_THREADS);
+            if (ATM && grp == 0) {
+                // this thread's user row -> its TMEM lane, columns [0, KP / 2): pairs of consecutive bf16 K elements per column
+                mbar_wait(A_EMPTY, (ublk & 1) ^ 1);            // the previous block's MMAs no longer read A
+                tc_fence_after();
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.ubf + (int64_t)(valid ? q : 0) * KP);
+#pragma unroll
+                for (int j = 0; j < KP / 16; j++) {
+                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+                    if (valid) { lo = __ldg(src + 2 * j); hi = __ldg(src + 2 * j + 1); }
+                    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    tmem_st8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 8), w);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(A_FULL);
+            }
             int cnt = 0;                              // filled logical slots of my row
             float thresh = (valid && p.debug_mode != 1) ? NEG : CUDART_INF_F;   // upper bound of everything dropped so far
             const uint32_t my_key = ckey + ROWB * (uint32_t)row, my_idx = cidx + ROWB * (uint32_t)row;
@@ -359,12 +447,12 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
             for (int t = 0; t < n_tiles; t++, tile++) {
                 const int acc = tile % NACC;
-                if (NG == 2 && (acc & 1) != grp) continue;
+                if (NG == 2 && (int)(tile & 1u) != grp) continue;
                 long long t0 = prof ? clock64() : 0;
                 mbar_wait(ACC_FULL(acc), (tile / NACC) & 1);
                 tc_fence_after();
                 if (prof) c_wait += clock64() - t0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(C::ACC0 + acc * BN);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 64) {
                     float v[64];
@@ -435,7 +523,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ACC_EMPTY(acc));
+                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_cluster(mapa_cluster(ACC_EMPTY(acc), 0)); else mbar_arrive(ACC_EMPTY(acc)); }
             }
             // final compaction: every row ends with its <= KC best unmasked candidates in logical slots 0..cnt-1
             __syncwarp();
@@ -533,8 +621,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) cluster_sync_all(); else __syncthreads();     // nobody leaves while the peer may still signal its barriers
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------- preparation kernels
@@ -645,29 +733,43 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
 
 struct TcMaps { CUtensorMap a, b, at, bt; };
 
-template <int KP, bool HAS_BIAS, int NG>
+template <int KP, bool HAS_BIAS, int NG, bool PAIR, bool ATM>
 static int launch_tc3(const TcMaps &m, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    auto kern = score_topk_tc_kernel<KP, HAS_BIAS, NG>;
-    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<KP, NG>::SMEM));
-    int grid = sm_count();
-    if (grid > n_mblocks) grid = n_mblocks;
-    kern<<<grid, TcCfg<KP, NG>::THREADS, TcCfg<KP, NG>::SMEM, st>>>(m.a, m.b, m.at, m.bt, p);
+    using C = TcCfg<KP, NG, PAIR, ATM>;
+    auto kern = score_topk_tc_kernel<KP, HAS_BIAS, NG, PAIR, ATM>;
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if (!PAIR) {
+        int grid = sm_count();
+        if (grid > n_mblocks) grid = n_mblocks;
+        kern<<<grid, C::THREADS, C::SMEM, st>>>(m.a, m.b, m.at, m.bt, p);
+    } else {
+        // clusters of two CTAs (one TPC): a cluster scores two user blocks against every item tile
+        int clusters = sm_count() / 2;
+        if (clusters > (n_mblocks + 1) / 2) clusters = (n_mblocks + 1) / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        EB_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.at, m.bt, p));
+    }
     EB_CUDA(cudaGetLastError());
     return EB_OK;
 }
 
-template <int KP, int NG>
+template <int KP, int NG, bool PAIR, bool ATM>
 static int launch_tc(void *ubf, void *vbf, const TcParams &p, int n_mblocks, cudaStream_t st) {
-    using C = TcCfg<KP, NG>;
+    using C = TcCfg<KP, NG, PAIR, ATM>;
     TcMaps m;
     // a tile without full blocks (KP = 16 / 32) still needs valid descriptors in the unused slots
     const uint32_t bc = C::KB ? 64 : C::KT, tc = C::KT ? C::KT : 64;
     if (int rc = make_map(&m.a, ubf, (uint64_t)p.n_sel, KP, bc, TC_BM)) return rc;
-    if (int rc = make_map(&m.b, vbf, (uint64_t)p.n_items, KP, bc, C::BN)) return rc;
+    if (int rc = make_map(&m.b, vbf, (uint64_t)p.n_items, KP, bc, C::BNL)) return rc;
     if (int rc = make_map(&m.at, ubf, (uint64_t)p.n_sel, KP, tc, TC_BM)) return rc;
-    if (int rc = make_map(&m.bt, vbf, (uint64_t)p.n_items, KP, tc, C::BN)) return rc;
+    if (int rc = make_map(&m.bt, vbf, (uint64_t)p.n_items, KP, tc, C::BNL)) return rc;
     const bool hb = p.bias != nullptr && !p.bias_folded;    // epilogue adds the bias only when it is not folded into the MMA
-    return hb ? launch_tc3<KP, true, NG>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG>(m, p, n_mblocks, st);
+    return hb ? launch_tc3<KP, true, NG, PAIR, ATM>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG, PAIR, ATM>(m, p, n_mblocks, st);
 }
 
 }  // namespace eb
@@ -724,7 +826,7 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     TcParams p{};
     p.U = U; p.V = V; p.bias = item_bias; p.d = d; p.ld = ld; p.n_items = n_items;
     p.mask_indptr = mask_indptr; p.mask_indices = mask_indices; p.user_begin = user_begin; p.n_sel = (int32_t)n_sel; p.k = k;
-    p.unorm = unorm; p.vstat = vstat; p.bmax_chunk = item_bias ? bmax : nullptr; p.bias_folded = fold ? 1 : 0;
+    p.ubf = ubf; p.unorm = unorm; p.vstat = vstat; p.bmax_chunk = item_bias ? bmax : nullptr; p.bias_folded = fold ? 1 : 0;
     p.out_idx = out_idx; p.out_val = out_val; p.flag_count = flag_count; p.flag_list = flag_list; p.dump = dump;
     // bf16 RN: |x~-x| <= 2^-9|x|  =>  |u~.v~ - u.v| <= (2^-8 + 2^-18) ||u|| ||v||; +2% for fp32 accumulation and re-rank rounding
     p.eps_scale = 1.02f * (1.f / 256.f);
@@ -734,12 +836,25 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
     // epilogue warpgroups: two by default (see TcCfg); EB_TC_NG=1 selects the single-group kernel for A/B measurements
     int ng = 2;
     { const char *e = getenv("EB_TC_NG"); if (e && atoi(e) == 1) ng = 1; }
+    // CTA pairs (tcgen05 cta_group::2, see TcCfg): EB_TC_PAIR=1 (two epilogue groups only)
+    bool pair = false;
+    { const char *e = getenv("EB_TC_PAIR"); if (e && atoi(e) == 1 && ng == 2) pair = true; }
+    // the user block in TMEM instead of shared memory (see TcCfg): EB_TC_ATM=1
+    bool atm = false;
+    { const char *e = getenv("EB_TC_ATM"); if (e && atoi(e) == 1 && ng == 2 && !pair) atm = true; }
     int rc;
     switch (L.KP) {
-#define EB_TC_CASE(K) case K: rc = ng == 2 ? launch_tc<K, 2>(ubf, vbf, p, n_mblocks, st) : launch_tc<K, 1>(ubf, vbf, p, n_mblocks, st); break;
-        EB_TC_CASE(16) EB_TC_CASE(32) EB_TC_CASE(64) EB_TC_CASE(80) EB_TC_CASE(96) EB_TC_CASE(128) EB_TC_CASE(144)
+#define EB_TC_CASE(K) case K: rc = ng == 2 ? launch_tc<K, 2, false, false>(ubf, vbf, p, n_mblocks, st)                           \
+                                          : launch_tc<K, 1, false, false>(ubf, vbf, p, n_mblocks, st); break;
+        // the measured-but-not-faster variants (CTA pairs, users in TMEM) exist for d = 64 and 128 with and without bias
+#define EB_TC_CASE_X(K) case K: rc = pair ? launch_tc<K, 2, true, false>(ubf, vbf, p, n_mblocks, st)                            \
+                                         : (atm ? launch_tc<K, 2, false, true>(ubf, vbf, p, n_mblocks, st)                     \
+                                                : (ng == 2 ? launch_tc<K, 2, false, false>(ubf, vbf, p, n_mblocks, st)         \
+                                                           : launch_tc<K, 1, false, false>(ubf, vbf, p, n_mblocks, st))); break;
+        EB_TC_CASE(16) EB_TC_CASE(32) EB_TC_CASE_X(64) EB_TC_CASE_X(80) EB_TC_CASE(96) EB_TC_CASE_X(128) EB_TC_CASE_X(144)
         EB_TC_CASE(160) EB_TC_CASE(192) EB_TC_CASE(208) EB_TC_CASE(224) EB_TC_CASE(256)
 #undef EB_TC_CASE
+#undef EB_TC_CASE_X
         default: return set_err(EB_ERR_ARG, "internal: unsupported padded K %d", L.KP);
     }
     if (rc) return rc;
@@ -753,7 +868,7 @@ extern "C" int eb_score_topk_tc_f32(const float *U, const float *V, const float 
         EB_CUDA(cudaMemcpyAsync(&flagged, flag_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EB_CUDA(cudaStreamSynchronize(st));
         stats_host[0] = flagged; stats_host[1] = L.KP;
-        if (p.prof) EB_CUDA(cudaMemcpy(stats_host + 2, p.prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (p.prof) EB_CUDA(cudaMemcpy(stats_host + 2, p.prof, 14 * sizeof(long long), cudaMemcpyDeviceToHost));
     }
     return EB_OK;
 }

@@ -249,7 +249,7 @@ def score_topk_tc(U, V, bias, d, k, mask_indptr=None, mask_indices=None, user_be
         check(lib().eb_score_topk_tc_f32(_ptr(U), _ptr(V), _ptr(bias), n_items, d, U.stride(0), _ptr(mask_indptr),
                                          _ptr(mask_indices), user_begin, n_sel, k, _ptr(idx), _ptr(val), _ptr(dmp),
                                          _ptr(ws), ws.numel(), ctypes.cast(st, ctypes.c_void_p) if stats else None, _stream(U)))
-    out = {"rechecked": int(st[0]), "kp": int(st[1]), "prof": [int(x) for x in st[2:10]]} if stats else {}
+    out = {"rechecked": int(st[0]), "kp": int(st[1]), "prof": [int(x) for x in st[2:16]]} if stats else {}
     if dump:
         out["dump"] = dmp
     return idx, val, out

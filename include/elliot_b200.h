@@ -455,7 +455,7 @@ int eb_gather_rows_peer_f32(float *const *shards, int n_shards, int32_t shard_ro
  * list with a rounding bound; users it cannot certify are re-done by the exact kernel inside
  * this call.  Contiguous user range only, k <= 16, d <= 256, mask rows sorted ascending.
  * dump (optional, tests): dense n_sel x n_items raw approximate scores.
- * stats_host (optional, host int64[16]): [0] users re-done exactly, [1] padded K, [2..9] cycle
+ * stats_host (optional, host int64[16]): [0] users re-done exactly, [1] padded K, [2..15] cycle
  * counters of CTA 0 when the environment variable EB_TC_PROF is set (profiling aid).
  * Asynchronous unless stats_host is given (reading the statistics back is the only synchronisation): the exact
  * re-check runs over a device-side count.  K is padded to a multiple of 16 (full 64-column blocks with the 128-byte

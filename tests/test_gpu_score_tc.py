@@ -11,10 +11,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True, params=["2", "1"], ids=["two_epilogue_groups", "one_epilogue_group"])
-def _epilogue_groups(request, monkeypatch):
-    """every test runs against both kernels: two epilogue warpgroups (the default) and the single-group one (EB_TC_NG=1)"""
-    monkeypatch.setenv("EB_TC_NG", request.param)
+@pytest.fixture(autouse=True, params=[("2", "0", "0"), ("1", "0", "0"), ("2", "1", "0"), ("2", "0", "1")],
+                ids=["two_epilogue_groups", "one_epilogue_group", "cta_pairs", "users_in_tmem"])
+def _kernel_variant(request, monkeypatch):
+    """every test runs against the four kernels: two epilogue warpgroups, one (EB_TC_NG=1), CTA pairs sharing each item
+    tile through tcgen05 cta_group::2 (EB_TC_PAIR=1), and the user block held in TMEM (EB_TC_ATM=1)"""
+    monkeypatch.setenv("EB_TC_NG", request.param[0])
+    monkeypatch.setenv("EB_TC_PAIR", request.param[1])
+    monkeypatch.setenv("EB_TC_ATM", request.param[2])
 
 
 def _tables(nu, ni, d, seed, scale=0.1, bias=True):

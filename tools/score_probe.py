@@ -34,6 +34,24 @@ if len(sys.argv) > 1 and sys.argv[1] == "ab":
             run(148 * 128 * 2, 100_000, 64, 10, 100, f"C2 ng={ng} dbg={dbg}")
             run(148 * 128 * 2, 2_000_000, 128, 10, 100, f"C5 ng={ng} dbg={dbg}")
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "pair":
+    # single CTAs against CTA pairs (tcgen05 cta_group::2: the item tile is fetched once per 256 users)
+    os.environ["EB_TC_PROF"] = "1"; os.environ["EB_TC_NG"] = "2"
+    for pair in ("0", "1"):
+        for dbg in ("0", "1"):
+            os.environ["EB_TC_PAIR"] = pair; os.environ["EB_TC_DEBUG"] = dbg
+            run(148 * 128 * 2, 100_000, 64, 10, 100, f"C2 pair={pair} dbg={dbg}")
+            run(148 * 128 * 2, 2_000_000, 128, 10, 100, f"C5 pair={pair} dbg={dbg}")
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "atm":
+    # the user block in shared memory against the user block in TMEM
+    os.environ["EB_TC_PROF"] = "1"; os.environ["EB_TC_NG"] = "2"; os.environ["EB_TC_PAIR"] = "0"
+    for atm in ("0", "1"):
+        for dbg in ("0", "1"):
+            os.environ["EB_TC_ATM"] = atm; os.environ["EB_TC_DEBUG"] = dbg
+            run(148 * 128 * 2, 100_000, 64, 10, 100, f"C2 atm={atm} dbg={dbg}")
+            run(148 * 128 * 2, 2_000_000, 128, 10, 100, f"C5 atm={atm} dbg={dbg}")
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "feed":
     # EB_TC_DEBUG=1: the epilogue only reads TMEM and takes the max (no inserts): the TMA/MMA pipeline's own pace
     os.environ["EB_TC_PROF"] = "1"
