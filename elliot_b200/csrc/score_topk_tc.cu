@@ -232,7 +232,9 @@ __device__ __noinline__ uint2 tc_compact_rows(uint32_t todo, uint32_t ckey, uint
     return make_uint2((uint32_t)cnt, __float_as_uint(thresh));
 }
 
-template <int KP, bool HAS_BIAS, int NGT, bool PAIR, bool ATM>
+// DBG = false compiles the instrumentation out (cycle counters, dense score dump, EB_TC_DEBUG modes): the clock reads alone
+// were 4 % of the kernel's instructions; the launcher picks DBG = true only when one of them is requested.
+template <int KP, bool HAS_BIAS, int NGT, bool PAIR, bool ATM, bool DBG>
 __global__ void __launch_bounds__(TcCfg<KP, NGT, PAIR, ATM>::THREADS, 1)
 score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmAt, const __grid_constant__ CUtensorMap tmBt, const TcParams p) {
@@ -240,7 +242,8 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int KB = C::KB, KT = C::KT, BN = C::BN, BNL = C::BNL, S = C::STAGES, NG = C::NG, NACC = C::NACC;
     constexpr int KCG = C::KCG, BUFG = C::BUFG;
     constexpr uint32_t ROWB = C::ROWB, GRPB = TC_BM * BUFG * 8;           // bytes per buffer row / per group (keys + ids)
-    const bool DUMP = p.dump != nullptr;
+    const bool DUMP = DBG && p.dump != nullptr;
+    const int debug_mode = DBG ? p.debug_mode : 0;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sA = sm;                                   // KB blocks of [128 rows x 128 B]
     uint8_t *sB = sA + C::A_BYTES;                      // S stages of KB blocks of [BN rows x 128 B]
@@ -286,7 +289,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ===================== TMA producer =====================
         if (elect_one_sync()) {
             int s = 0; uint32_t ph = 0; uint32_t it = 0;
-            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            const bool prof = DBG && p.prof != nullptr && blockIdx.x == 0;
             long long w_bempty = 0;
             const uint32_t a_full = PAIR ? mapa_cluster(A_FULL, 0) : A_FULL;
             for (int un = unit0; un < n_units; un += unit_step, it++) {
@@ -340,7 +343,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             };
             auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int s = 0; uint32_t ph = 0; uint32_t it = 0; uint32_t tile = 0;
-            const bool prof = p.prof != nullptr && blockIdx.x == 0;
+            const bool prof = DBG && p.prof != nullptr && blockIdx.x == 0;
             long long w_acc = 0, w_bfull = 0, w_afull = 0, t_all = prof ? clock64() : 0;
             for (int un = unit0; un < n_units; un += unit_step, it++) {
                 { const long long t0 = prof ? clock64() : 0; mbar_wait(A_FULL, it & 1); if (prof) w_afull += clock64() - t0; }
@@ -395,7 +398,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t cidx = ckey + TC_BM * BUFG * 4;
         uint32_t tile = 0;
         long long c_wait = 0, c_ld = 0, c_scan = 0, c_comp = 0, c_rank = 0, n_comp = 0, n_slow = 0, n_grp = 0;
-        const bool prof = p.prof != nullptr && warp == 2;
+        const bool prof = DBG && p.prof != nullptr && warp == 2;
         constexpr int EPI_THREADS = 128 * NG;
         uint32_t ublk = 0;                            // user blocks this CTA has started
         for (int un = unit0; un < n_units; un += unit_step, ublk++) {
@@ -432,7 +435,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) mbar_arrive(A_FULL);
             }
             int cnt = 0;                              // filled logical slots of my row
-            float thresh = (valid && p.debug_mode != 1) ? NEG : CUDART_INF_F;   // upper bound of everything dropped so far
+            float thresh = (valid && debug_mode != 1) ? NEG : CUDART_INF_F;   // upper bound of everything dropped so far
             const uint32_t my_key = ckey + ROWB * (uint32_t)row, my_idx = cidx + ROWB * (uint32_t)row;
             // invariant: logical slots >= cnt hold -inf keys
 #pragma unroll 8
@@ -478,16 +481,17 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                     float bm0 = 0.f, bm1 = 0.f;
                     if (HAS_BIAS) { bm0 = __ldg(p.bmax_chunk + (col0 >> 5)); bm1 = __ldg(p.bmax_chunk + min((col0 >> 5) + 1, (p.n_items - 1) >> 5)); }
-                    const float m64 = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) + bm0, fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])) + bm1);
+                    const float m64 = HAS_BIAS ? fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) + bm0, fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])) + bm1)
+                                               : fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                     if (!__any_sync(0xffffffffu, m64 > thresh)) { if (prof) c_scan += clock64() - t2; continue; }
-                    n_slow++;
+                    if (DBG) n_slow++;
 #pragma unroll
                     for (int s8 = 0; s8 < 8; s8++) {
                         const float bm = s8 < 4 ? bm0 : bm1;
-                        if (!__any_sync(0xffffffffu, g[s8] + bm > thresh)) continue;
-                        n_grp++;
+                        if (!__any_sync(0xffffffffu, (HAS_BIAS ? g[s8] + bm : g[s8]) > thresh)) continue;
+                        if (DBG) n_grp++;
                         const uint32_t todo = __ballot_sync(0xffffffffu, cnt > BUFG - TC_SLACK);
-                        if (todo) { long long t3 = prof ? clock64() : 0; n_comp += __popc(todo); if (p.debug_mode == 2) { if (cnt > BUFG - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
+                        if (todo) { long long t3 = prof ? clock64() : 0; if (DBG) n_comp += __popc(todo); if (debug_mode == 2) { if (cnt > BUFG - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
                         // Append survivors one at a time, largest first: locate the group's max with static
                         // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
                         // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
@@ -600,7 +604,7 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const float un = __shfl_sync(0xffffffffu, my_unorm, r);
                 const float eps = p.eps_scale * un * vmax_n + 1e-6f * un * vmax_n + 4e-5f * bmax_a;   // bias: hi+lo bf16 split, 2^-17 rel
                 const float kth = __shfl_sync(0xffffffffu, sv, p.k - 1);
-                const bool certified = !(rthresh > NEG) || (kth > rthresh + eps) || p.debug_mode != 0;
+                const bool certified = !(rthresh > NEG) || (kth > rthresh + eps) || debug_mode != 0;
                 if (lane < p.k) {
                     const bool ok = lane < rcount && sv > NEG;
                     p.out_idx[(int64_t)rq * p.k + lane] = ok ? si : -1;
@@ -733,10 +737,10 @@ static TcLayout tc_layout(int64_t n_sel, int32_t n_items, int d, bool fold) {
 
 struct TcMaps { CUtensorMap a, b, at, bt; };
 
-template <int KP, bool HAS_BIAS, int NG, bool PAIR, bool ATM>
+template <int KP, bool HAS_BIAS, int NG, bool PAIR, bool ATM, bool DBG>
 static int launch_tc3(const TcMaps &m, const TcParams &p, int n_mblocks, cudaStream_t st) {
     using C = TcCfg<KP, NG, PAIR, ATM>;
-    auto kern = score_topk_tc_kernel<KP, HAS_BIAS, NG, PAIR, ATM>;
+    auto kern = score_topk_tc_kernel<KP, HAS_BIAS, NG, PAIR, ATM, DBG>;
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     if (!PAIR) {
         int grid = sm_count();
@@ -769,7 +773,12 @@ static int launch_tc(void *ubf, void *vbf, const TcParams &p, int n_mblocks, cud
     if (int rc = make_map(&m.at, ubf, (uint64_t)p.n_sel, KP, tc, TC_BM)) return rc;
     if (int rc = make_map(&m.bt, vbf, (uint64_t)p.n_items, KP, tc, C::BNL)) return rc;
     const bool hb = p.bias != nullptr && !p.bias_folded;    // epilogue adds the bias only when it is not folded into the MMA
-    return hb ? launch_tc3<KP, true, NG, PAIR, ATM>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG, PAIR, ATM>(m, p, n_mblocks, st);
+    // the lean kernel exists for the default layout only; the others always carry the instrumentation
+    constexpr bool LEAN = NG == 2 && !PAIR && !ATM;
+    const bool dbg = p.dump != nullptr || p.prof != nullptr || p.debug_mode != 0;
+    if (LEAN && !dbg)
+        return hb ? launch_tc3<KP, true, NG, PAIR, ATM, !LEAN>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG, PAIR, ATM, !LEAN>(m, p, n_mblocks, st);
+    return hb ? launch_tc3<KP, true, NG, PAIR, ATM, true>(m, p, n_mblocks, st) : launch_tc3<KP, false, NG, PAIR, ATM, true>(m, p, n_mblocks, st);
 }
 
 }  // namespace eb
