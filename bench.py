@@ -625,15 +625,23 @@ def main():
         US = U.clone(); c = [0]
         items.barrier()
 
+        grouped = world > 4
+
         def st():
-            ops.bpr_step_sampled_peer_f32(US, items.ptrs, bias.ptr_array(), items.shard_rows, D, N_USERS, NIS, ipS, ixS, BATCH,
-                                          seed, c[0] * BATCH, *HP, filter=fS)
+            if not grouped:      # up to 3 peers: ONE kernel samples, gathers over NVLink, updates
+                ops.bpr_step_sampled_peer_f32(US, items.ptrs, bias.ptr_array(), items.shard_rows, D, N_USERS, NIS, ipS, ixS, BATCH,
+                                              seed, c[0] * BATCH, *HP, filter=fS)
+            else:                # more: sample, bucket the triples by the owners of (i, j), then the step over peer memory
+                tu, ti, tj = ops.bpr_sample_philox(N_USERS, NIS, ipS, ixS, BATCH, seed, c[0] * BATCH, filter=fS)
+                tu, ti, tj = ops.group_by_owner([tu, ti, tj], 1, 2, items.shard_rows, rank, world)
+                ops.bpr_step_peer_f32(US, items.ptrs, bias.ptr_array(), items.shard_rows, D, NIS, tu, ti, tj, *HP)
             c[0] += 1
         ms = timed(st, 10, warm=3)
         out = {"metric": "bpr_triples_per_sec_sharded_items", "value": BATCH * world / (ms * 1e-3), "unit": "triples/s", "ms": ms,
                "per_gpu": BATCH / (ms * 1e-3),
                "config": {"workload": f"{N_USERS} users/GPU, {NIS} items row-sharded over {world} GPUs, d={D}, {BATCH} triples/step/GPU; item rows "
-                                      f"loaded and atomically updated in their owner's memory over NVLink inside the training kernel ({items.buf.kind})",
+                                      f"loaded and atomically updated in their owner's memory over NVLink inside the training kernel ({items.buf.kind})"
+                                      + ("; triples bucketed by the owners of (i, j) first (more than 4 GPUs)" if grouped else ""),
                           "nvlink_bytes_per_triple_each_way": 2 * (D * 4 + 4) * (world - 1) / world},
                "finite": bool(torch.isfinite(items.local).all().item())}
         items.close(); bias.close()

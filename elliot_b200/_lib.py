@@ -121,6 +121,8 @@ SIGNATURES = {
                                      c_i64, c_void, c_i64, c_void]),
     "eb_neumf_scatter_peer": (c_int, [c_void, c_i64, c_void, c_void, c_int, c_i32, c_i64, c_int, c_void, c_void, c_i64, c_void,
                                       c_i64, c_void, c_i64, c_void, c_void, c_void]),
+    "eb_group_by_owner_i32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_i64, c_i32, c_int, c_int, c_void, c_void, c_void, c_void,
+                                      c_void]),
     "eb_gather_rows_peer_f32": (c_int, [c_void, c_int, c_i32, c_i64, c_void, c_i64, c_int, c_void, c_i64, c_void]),
     "eb_score_topk_tc_workspace_bytes": (c_size, [c_i64, c_i32, c_int]),
     "eb_score_topk_tc_f32": (c_int, [c_void, c_void, c_void, c_i32, c_int, c_int, c_void, c_void, c_i32, c_i64, c_int,

@@ -254,6 +254,104 @@ extern "C" int eb_neumf_scatter_peer(const float *Umf, int64_t ldu, float *const
     return EB_OK;
 }
 
+// ---------------------------------------------------------------- batches ordered by owner
+// Measured on 8 B200s (tools/peer_fanout_probe.py, profiles/r2c_peer_fanout_n8.json): 256-byte rows gathered at random from ONE
+// peer arrive at 630 GB/s; the same rows drawn from all 7 peers interleaved arrive at 44 GB/s (with the other 7 GPUs idle, so
+// it is the requester, not the fabric; three peers interleaved, as on 4 GPUs, still run at 615 GB/s); the same ids GROUPED by
+// owner — every rank starting at its right-hand neighbour — arrive at 548 GB/s.  A batch whose rows live on more than four
+// peers is therefore bucketed by owner before the peer kernels see it: a counting sort over <= 64 keys
+//     key = ((owner(id1) - rank) mod W) [* W + ((owner(id2) - rank) mod W)]
+// (order inside a bucket is arbitrary: the samples of a step are exchangeable).
+struct GroupParams {
+    const int32_t *a, *b, *c;      // three 32-bit payload arrays that travel together (b, c may be null)
+    const int32_t *id1, *id2;      // the arrays holding the row ids (id2 null: one id per element)
+    int64_t n;
+    int32_t shard_rows;
+    int rank, world;
+    int32_t *out_a, *out_b, *out_c;
+    int32_t *counts, *cursor;      // [64] each
+};
+
+__device__ __forceinline__ int group_key(const GroupParams &p, int64_t e) {
+    const int w = p.world;
+    int o1 = p.id1[e] / p.shard_rows; o1 = o1 >= w ? w - 1 : o1;
+    int k = (o1 - p.rank + w) % w;
+    if (p.id2) {
+        int o2 = p.id2[e] / p.shard_rows; o2 = o2 >= w ? w - 1 : o2;
+        k = k * w + (o2 - p.rank + w) % w;
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(256) group_count_kernel(const GroupParams p) {
+    __shared__ int hist[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[group_key(p, e)], 1);
+    __syncthreads();
+    if (threadIdx.x < 64 && hist[threadIdx.x]) atomicAdd(p.counts + threadIdx.x, hist[threadIdx.x]);
+}
+
+__global__ void group_scan_kernel(const GroupParams p) {
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; k++) { p.cursor[k] = run; run += p.counts[k]; }
+    }
+}
+
+constexpr int GROUP_CHUNK = 2048;      // elements per block pass: one global reservation per key and chunk
+
+__global__ void __launch_bounds__(256) group_scatter_kernel(const GroupParams p) {
+    __shared__ int hist[64], base[64];
+    const int64_t n_chunks = (p.n + GROUP_CHUNK - 1) / GROUP_CHUNK;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+        __syncthreads();
+        int key[GROUP_CHUNK / 256], slot[GROUP_CHUNK / 256];
+#pragma unroll
+        for (int j = 0; j < GROUP_CHUNK / 256; j++) {
+            const int64_t e = ch * GROUP_CHUNK + j * 256 + threadIdx.x;
+            key[j] = e < p.n ? group_key(p, e) : -1;
+            slot[j] = key[j] >= 0 ? atomicAdd(&hist[key[j]], 1) : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) base[threadIdx.x] = hist[threadIdx.x] ? atomicAdd(p.cursor + threadIdx.x, hist[threadIdx.x]) : 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < GROUP_CHUNK / 256; j++) {
+            const int64_t e = ch * GROUP_CHUNK + j * 256 + threadIdx.x;
+            if (key[j] < 0) continue;
+            const int64_t o = (int64_t)base[key[j]] + slot[j];
+            p.out_a[o] = p.a[e];
+            if (p.b) p.out_b[o] = p.b[e];
+            if (p.c) p.out_c[o] = p.c[e];
+        }
+    }
+}
+
+extern "C" int eb_group_by_owner_i32(const int32_t *a, const int32_t *b, const int32_t *c, int key1, int key2, int64_t n,
+                                     int32_t shard_rows, int rank, int world, int32_t *out_a, int32_t *out_b, int32_t *out_c,
+                                     int32_t *work, void *stream) {
+    EB_ARG(a && out_a && work && n >= 0 && n < (1ll << 31), "null pointer or bad size");
+    EB_ARG((b == nullptr) == (out_b == nullptr) && (c == nullptr) == (out_c == nullptr), "payload arrays and outputs must match");
+    EB_ARG(shard_rows >= 1 && world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad shard geometry (world <= 8)");
+    const int32_t *arr[3] = {a, b, c};
+    EB_ARG(key1 >= 0 && key1 <= 2 && arr[key1] && key2 >= -1 && key2 <= 2 && (key2 < 0 || arr[key2]), "key1 / key2 name the id arrays (0..2)");
+    if (n == 0) return EB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    EB_CUDA(cudaMemsetAsync(work, 0, 128 * sizeof(int32_t), st));
+    GroupParams p{a, b, c, arr[key1], key2 >= 0 ? arr[key2] : nullptr, n, shard_rows, rank, world, out_a, out_b, out_c, work, work + 64};
+    group_count_kernel<<<pgrid(n), 256, 0, st>>>(p);
+    group_scan_kernel<<<1, 32, 0, st>>>(p);
+    const int64_t n_chunks = (n + GROUP_CHUNK - 1) / GROUP_CHUNK;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    group_scatter_kernel<<<(unsigned)(n_chunks < cap ? n_chunks : cap), 256, 0, st>>>(p);
+    EB_CUDA(cudaGetLastError());
+    return EB_OK;
+}
+
 extern "C" int eb_gather_rows_peer_f32(float *const *shards, int n_shards, int32_t shard_rows, int64_t ld, const int32_t *ids, int64_t n,
                                        int width, float *out, int64_t ldo, void *stream) {
     PeerTab T;

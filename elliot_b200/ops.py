@@ -728,6 +728,21 @@ def neumf_scatter_peer(Umf, I_shards, GI_shards, shard_rows, ldi, f, u, it, dpm,
           _ptr(dpm), dpm.stride(0), _ptr(dx0), dx0.stride(0), _ptr(dUmf), _ptr(dUmlp))
 
 
+def group_by_owner(arrays, key1, key2, shard_rows, rank, world):
+    """Reorder up to three 32-bit arrays that travel together so that elements whose row (arrays[key1], and arrays[key2] if
+    key2 >= 0) lives on the same owner are adjacent, starting with rank+1's rows (see eb_group_by_owner_i32: with more than four
+    GPUs a peer kernel fed in this order moves rows 12x faster).  float32 payloads are carried bit for bit.  Returns new tensors."""
+    arrays = list(arrays) + [None] * (3 - len(arrays))
+    _need_cuda(*[x for x in arrays if x is not None])
+    views = [None if x is None else x.view(torch.int32) for x in arrays]
+    n = views[0].numel()
+    outs = [None if v is None else torch.empty_like(v) for v in views]
+    work = torch.empty(128, dtype=torch.int32, device=views[0].device)
+    _call("eb_group_by_owner_i32", views[0], _ptr(views[0]), _ptr(views[1]), _ptr(views[2]), key1, key2, n, shard_rows, rank, world,
+          _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(work))
+    return [None if o is None else o.view(x.dtype) for o, x in zip(outs, arrays)]
+
+
 def gather_rows_peer_f32(shards, shard_rows, ld, ids, width, out=None):
     _need_cuda(ids, out); _chk_idx(ids)
     sa, n = _ptr_array(shards)

@@ -219,3 +219,34 @@ def test_sharded_neumf_single_rank_tracks_the_ordinary_model():
     i1, v1 = ref.get_recs_topk(0, 64, 5, indptr, indices); i2, v2 = sh.get_recs_topk(0, 64, 5, indptr, indices)
     assert (i1 == i2).float().mean().item() > 0.98 and torch.allclose(v1, v2, atol=1e-4)
     sh.close()
+
+
+@pytest.mark.parametrize("two_ids", [False, True])
+def test_group_by_owner_is_a_permutation_ordered_by_rotated_owner(two_ids):
+    """eb_group_by_owner_i32: the three arrays travel together, the elements come out bucketed by
+    ((owner(i) - rank) mod W [, (owner(j) - rank) mod W]) in ascending order, nothing is lost or duplicated."""
+    dev = DEV
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    n, world, rank, shard_rows = 300_001, 8, 3, 12_345
+    n_items = shard_rows * world - 7                                   # the last shard is short
+    u = torch.randint(0, 1_000_000, (n,), device=dev, generator=g, dtype=torch.int32)
+    i = torch.randint(0, n_items, (n,), device=dev, generator=g, dtype=torch.int32)
+    j = torch.randint(0, n_items, (n,), device=dev, generator=g, dtype=torch.int32)
+    y = torch.rand(n, device=dev, generator=g)
+    if two_ids:
+        ou, oi, oj = ops.group_by_owner([u, i, j], 1, 2, shard_rows, rank, world)
+        key = ((oi // shard_rows - rank) % world) * world + (oj // shard_rows - rank) % world
+        before = torch.stack([u, i, j], 1); after = torch.stack([ou, oi, oj], 1)
+    else:
+        ou, oi, oy = ops.group_by_owner([u, i, y], 1, -1, shard_rows, rank, world)
+        assert oy.dtype == torch.float32
+        key = (oi // shard_rows - rank) % world
+        before = torch.stack([u, i, y.view(torch.int32)], 1); after = torch.stack([ou, oi, oy.view(torch.int32)], 1)
+    assert (key[1:] >= key[:-1]).all()
+    # exact multiset equality through a full lexicographic sort
+    def lex(t):
+        t = t.cpu().long()
+        for c in (2, 1, 0):
+            t = t[torch.argsort(t[:, c], stable=True)]
+        return t
+    assert torch.equal(lex(before), lex(after))
