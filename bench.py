@@ -634,8 +634,14 @@ def main():
             else:                # more: sample, bucket the triples by the owners of (i, j), then the step over peer memory
                 tu, ti, tj = ops.bpr_sample_philox(N_USERS, NIS, ipS, ixS, BATCH, seed, c[0] * BATCH, filter=fS)
                 tu, ti, tj = ops.group_by_owner([tu, ti, tj], 1, 2, items.shard_rows, rank, world)
-                ops.bpr_step_peer_f32(US, items.ptrs, bias.ptr_array(), items.shard_rows, D, NIS, tu, ti, tj, *HP)
+                ops.bpr_step_peer_f32(US, items.ptrs, bias.ptr_array(), items.shard_rows, D, NIS, tu, ti, tj, *HP, _variant=variant[0])
             c[0] += 1
+        variant, trial = [0], {}
+        if grouped:              # which row staging crosses 7 peers better is measured, not assumed: registers (16) or shared memory (32)
+            for v in (16, 32):
+                variant[0] = v
+                trial[v] = timed(st, 3, warm=2)
+            variant[0] = min(trial, key=trial.get)
         ms = timed(st, 10, warm=3)
         out = {"metric": "bpr_triples_per_sec_sharded_items", "value": BATCH * world / (ms * 1e-3), "unit": "triples/s", "ms": ms,
                "per_gpu": BATCH / (ms * 1e-3),
@@ -644,6 +650,8 @@ def main():
                                       + ("; triples bucketed by the owners of (i, j) first (more than 4 GPUs)" if grouped else ""),
                           "nvlink_bytes_per_triple_each_way": 2 * (D * 4 + 4) * (world - 1) / world},
                "finite": bool(torch.isfinite(items.local).all().item())}
+        if grouped:
+            out["config"]["row_staging_trial_ms"] = {"registers": trial[16], "shared_memory": trial[32]}
         items.close(); bias.close()
         return out
     if world > 1:

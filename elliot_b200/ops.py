@@ -675,14 +675,16 @@ def _ptr_array(ptrs):
     return (ctypes.c_void_p * len(vals))(*vals), len(vals)
 
 
-def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None):
-    """BPR step on materialised triples, item table + biases row-sharded (shard s = rows [s*shard_rows, (s+1)*shard_rows))."""
+def bpr_step_peer_f32(U, V_shards, b_shards, shard_rows, d, n_items, tu, ti, tj, lr, reg_u, reg_b, reg_pos, reg_neg, loss=None,
+                      _variant=0):
+    """BPR step on materialised triples, item table + biases row-sharded (shard s = rows [s*shard_rows, (s+1)*shard_rows)).
+    _variant (profiling): 16 forces the register-staged kernel, 32 the shared-memory-staged one."""
     _need_cuda(U, tu, ti, tj, loss); _chk_idx(tu, ti, tj)
     va, n = _ptr_array(V_shards); ba, nb = _ptr_array(b_shards)
     assert n == nb and U.dtype == torch.float32 and U.stride(1) == 1
     with torch.cuda.device(U.device):
         check(lib().eb_bpr_step_peer_f32(_ptr(U), va, ba, n, shard_rows, d, U.stride(0), n_items, _ptr(tu), _ptr(ti), _ptr(tj),
-                                         tu.numel(), lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), 0, _stream(U)))
+                                         tu.numel(), lr, reg_u, reg_b, reg_pos, reg_neg, _ptr(loss), _variant, _stream(U)))
 
 
 def bpr_step_sampled_peer_f32(U, V_shards, b_shards, shard_rows, d, n_users, n_items, indptr, indices, n, seed, first, lr, reg_u,
