@@ -98,13 +98,19 @@ template <int KP, int NG_, bool PAIR_ = false, bool ATM_ = false> struct TcCfg {
     // keeps one accumulator per group — the groups alternate, so the MMA of one tile still overlaps the scan of the other
     static constexpr bool ATM = ATM_;
     static_assert(!(ATM && (PAIR || NG != 2)), "A-in-TMEM is built for the two-group single-CTA kernel");
-    static constexpr int NACC = ATM ? 3 : (PAIR ? NG : 2 * NG);
+    // items per tile of the two-group kernel.  64 (eight accumulators, four per group: deeper MMA / scan decoupling) was measured
+    // SLOWER than 128 (four accumulators): C2 probe 5.22 vs 4.92 ms, C5 slice 24.7 vs 20.0 ms — the per-tile hand-shakes cost more
+    // than the slack buys (profiles/r2c_score_bn64.log).  -DEB_TC_BN2=64 rebuilds that variant.
+#ifndef EB_TC_BN2
+#define EB_TC_BN2 128
+#endif
+    static constexpr int NACC = ATM ? 3 : (PAIR ? NG : (NG == 2 ? 512 / EB_TC_BN2 : 2 * NG));
     static constexpr int ACC0 = ATM ? 128 : 0;               // first accumulator column
     static constexpr int KCG = TC_KC / NG;                   // candidates kept per row and group
     static constexpr int BUFG = TC_BUF / NG;                 // buffer slots per row and group
     static constexpr int ROWB = BUFG * 4;                    // bytes per buffer row (keys; the ids follow in a second array)
     static constexpr int BN = PAIR ? (KP <= 208 ? 256 : 128)
-                                   : (NG == 2 ? (KP <= 208 ? 128 : 64)
+                                   : (NG == 2 ? (ATM ? 128 : (KP <= 208 ? EB_TC_BN2 : 64))
                                               : (KP <= 128 ? 256 : (KP <= 208 ? 128 : 64)));   // items per tile (UMMA N)
     static_assert(ACC0 + NACC * BN <= 512, "accumulators exceed TMEM");
     static constexpr int TMEM_COLS = ATM ? 512 : NACC * BN;  // 256 or 512: a power of two
