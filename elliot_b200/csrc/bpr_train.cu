@@ -517,10 +517,35 @@ static int launch_hogwild_t(const HogwildParams &p, int reserve_sms, cudaStream_
     return EB_OK;
 }
 
+// EB_L2_PERSIST=1: mark the item table's address range as persisting in L2 for the launch's stream (cudaAccessPolicyWindow) when it
+// fits the device's persisting carve-out — the table is hit by two of every triple's three row accesses, the user table and the
+// CSR are streamed once.  An A/B switch: the measured effect decides the default.
+static void item_table_l2_window(const HogwildParams &p, cudaStream_t st) {
+    static const int env = [] { const char *e = getenv("EB_L2_PERSIST"); return e ? atoi(e) : 0; }();
+    if (!env || !p.V) return;
+    static int max_persist = -1, max_window = 0;
+    if (max_persist < 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    }
+    const size_t bytes = (size_t)p.n_items * (size_t)p.ld * sizeof(float);
+    if (max_persist <= 0 || bytes > (size_t)max_persist || bytes > (size_t)max_window) return;
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = (void *)p.V;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
 template <bool SAMPLE>
 static int launch_hogwild(const HogwildParams &p, int dp, int flags, cudaStream_t st) {
     const bool atomic = !(flags & 1);
     const int reserve = (flags >> 8) & 0xff;
+    item_table_l2_window(p, st);
     if (use_stage(dp, flags, false)) {
         switch (dp) {
             case 32: return launch_stage_t<32, SAMPLE, false>(p, reserve, st);
