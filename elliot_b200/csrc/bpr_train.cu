@@ -528,16 +528,17 @@ static void item_table_l2_window(const HogwildParams &p, cudaStream_t st) {
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
     }
     const size_t bytes = (size_t)p.n_items * (size_t)p.ld * sizeof(float);
     if (max_persist <= 0 || bytes > (size_t)max_persist || bytes > (size_t)max_window) return;
+    static size_t carved = 0;                 // the carve-out is sized to the table, not to the device maximum
+    if (carved != bytes) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes); carved = bytes; }
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = (void *)p.V;
     attr.accessPolicyWindow.num_bytes = bytes;
     attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    attr.accessPolicyWindow.missProp = env == 2 ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
