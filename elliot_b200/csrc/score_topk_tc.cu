@@ -5,16 +5,18 @@
 // MFModel.get_user_predictions (BPRMF_model.py:70-85) at catalogue scale: the (users x items)
 // score matrix is never materialised.
 //
-// Pipeline per CTA (persistent, one CTA per SM, 6 warps):
+// Pipeline per CTA (persistent, one CTA per SM, 10 warps in the default layout):
 //   warp 0   TMA producer : A tile (128 users x KP, bf16, once per user block) and a ring of
-//                           B tiles (BN items x KP) via cp.async.bulk.tensor, 128B swizzle
-//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                           (M=128, N=BN, K=16) into one of two TMEM accumulators (2 x BN cols)
-//   warps 2-5 epilogue    : thread r owns user row r: tcgen05.ld 32 columns at a time, a
-//                           running threshold filters all but the current top-KC approximate
-//                           scores (max-of-32 fast path), survivors are checked against the
-//                           train CSR and kept in a per-row candidate list in shared memory.
-// After the last item tile each warp re-scores its rows' KC=32 candidates EXACTLY in fp32
+//                           B tiles (BN items x KP) via cp.async.bulk.tensor, 128B swizzle (+ a narrower-swizzle K tail)
+//   warp 1   MMA issuer   : one ELECTED lane (elect.sync) issues tcgen05.mma.cta_group::1.kind::f16
+//                           (M=128, N=BN, K=16) into one of four TMEM accumulators (4 x 128 columns)
+//   warps 2-5, 6-9        : two epilogue warpgroups (tiles alternate between them, two accumulators each); thread r of a
+//                           group owns user row r: tcgen05.ld 64 columns at a time, a running threshold filters all but the
+//                           group's current top-16 approximate scores (max-tree fast path), survivors are checked against
+//                           the train CSR (block's mask rows cached in shared memory) and kept in a per-row candidate list.
+// Variants behind template switches (TcCfg): one epilogue group (NG = 1), CTA pairs on tcgen05 cta_group::2 (PAIR), the user
+// block in TMEM (ATM), instrumentation (DBG).  DESIGN.md 4.1 has the measurements that chose the default.
+// After the last item tile each warp re-scores its rows' <= 32 candidates (16 per group) EXACTLY in fp32
 // (same summation order as score_topk.cu), sorts them with a 32-lane bitonic network
 // (score desc, index asc) and certifies the result:
 //      every item not in the list has approx score <= tau (final threshold), so its exact
