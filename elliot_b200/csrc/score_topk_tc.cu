@@ -66,7 +66,6 @@ struct TcParams {
 };
 
 constexpr int TC_BUF = 64;        // append-buffer slots per user row over all epilogue groups (top-KC kept + pending)
-constexpr int TC_SLACK = 8;       // a row is compacted before a group of 8 columns if fewer than 8 slots are free
 
 // KP = padded K (multiple of 16): KB full 64-wide blocks (one 128-byte swizzle atom each) + a tail of KT = 0, 16 or 32
 // columns in its own narrower-swizzle block.  (A 48-column tail is rounded up to a full block by the host.)  Padding K
@@ -498,8 +497,6 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         const float bm = s8 < 4 ? bm0 : bm1;
                         if (!__any_sync(0xffffffffu, (HAS_BIAS ? g[s8] + bm : g[s8]) > thresh)) continue;
                         if (DBG) n_grp++;
-                        const uint32_t todo = __ballot_sync(0xffffffffu, cnt > BUFG - TC_SLACK);
-                        if (todo) { long long t3 = prof ? clock64() : 0; if (DBG) n_comp += __popc(todo); if (debug_mode == 2) { if (cnt > BUFG - TC_SLACK) { cnt = 0; thresh = 0.3f; } } else compact(todo); if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; } }
                         // Append survivors one at a time, largest first: locate the group's max with static
                         // compares, append it (branch-free), knock it out and re-evaluate the group max.  Almost
                         // always one round: ~45 instructions instead of ~150 for 8 unconditional append slots.
@@ -511,6 +508,16 @@ score_topk_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll 1
                         for (int round = 0; round < 8; round++) {
                             if (!__any_sync(0xffffffffu, gm > thresh)) break;
+                            // a row is compacted only when an append finds its buffer FULL (not 8 slots early): with 32 slots
+                            // and 16 kept that is 16 appends per compaction instead of 9-16
+                            const uint32_t todo = __ballot_sync(0xffffffffu, gm > thresh && cnt >= BUFG);
+                            if (todo) {
+                                long long t3 = prof ? clock64() : 0;
+                                if (DBG) n_comp += __popc(todo);
+                                if (debug_mode == 2) { if (cnt >= BUFG) { cnt = 0; thresh = 0.3f; } } else compact(todo);
+                                if (prof) { long long dt = clock64() - t3; c_comp += dt; c_scan -= dt; }
+                                if (!__any_sync(0xffffffffu, gm > thresh)) break;       // the thresholds just rose
+                            }
                             int am = 7;
 #pragma unroll
                             for (int c = 6; c >= 0; c--) am = (w8[c] == gm) ? c : am;      // first position holding the max
